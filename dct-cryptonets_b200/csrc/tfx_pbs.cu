@@ -1,0 +1,353 @@
+// tfx_pbs.cu — K1: batched programmable bootstrap (mod-switch, blind rotation, sample extract fused),
+// plus the BSK -> Fourier conversion and the FFT test hooks that share its transform.
+//
+// One CTA owns one ciphertext at a time (grid-stride over the batch).  The GLWE accumulator ((k+1) x N
+// torus words) lives in shared memory for the whole blind rotation.  The CTA is split into (k+1) groups of
+// M/8 threads; group r runs the forward FFTs of the digit polynomials of accumulator component r (levels in
+// sequence), multiplies them with the Fourier bootstrapping key rows (r, lvl, *) streamed from HBM/L2
+// in a thread-major layout (coalesced 16 B per lane), and keeps the (k+1) partial output spectra in
+// registers.  Partial spectra are exchanged through shared memory, then group c runs the inverse FFT of
+// output component c and adds the rounded result into the accumulator.
+// Replaces (upstream) concrete-cpu's bootstrap behind reference homomorphic_eval.py:70.
+#include "tfx_common.cuh"
+#include "tfx_internal.h"
+
+namespace tfx {
+
+template <int LOGN, int K> struct PbsCfg {
+    static constexpr int N = 1 << LOGN;
+    static constexpr int LOGM = LOGN - 1;
+    static constexpr int M = N / 2;
+    static constexpr int TPF = M / 8;
+    static constexpr int G = K + 1;
+    static constexpr int THREADS = G * TPF;
+    static constexpr int XB = (K > 1 ? K : 1) * M;     // exchange buffer (complex) per group
+    static constexpr size_t smem_bytes(int n) {
+        return (size_t)G * N * 8 + (size_t)G * XB * 16 + (size_t)M * 16 * 2 + (size_t)((n + 1 + 7) / 8 * 8) * 4;
+    }
+};
+
+struct PbsArgs {
+    const double2* bsk;        // [n][G][l][G][8][TPF]
+    const double2* twist;      // [M]
+    const double2* tw;         // [M]
+    const uint64_t* in;        // [B][n+1]
+    const uint64_t* luts;      // [T][N]
+    const uint32_t* lut_index; // [B]
+    uint64_t* out;             // [B][kN+1]
+    uint32_t n;
+    int base_log, level, mode;
+    uint64_t body_const;
+    uint32_t count;
+};
+
+template <int LOGN, int K>
+__global__ void __launch_bounds__(PbsCfg<LOGN, K>::THREADS, 1)
+pbs_kernel(PbsArgs a) {
+    using C = PbsCfg<LOGN, K>;
+    constexpr int N = C::N, M = C::M, LOGM = C::LOGM, TPF = C::TPF, G = C::G;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* acc = reinterpret_cast<uint64_t*>(smem_raw);                    // [G][N]
+    double2* xbuf = reinterpret_cast<double2*>(acc + (size_t)G * N);          // [G][XB]
+    double2* s_tw = xbuf + (size_t)G * C::XB;                                 // [M]
+    double2* s_twist = s_tw + M;                                              // [M]
+    uint32_t* s_ahat = reinterpret_cast<uint32_t*>(s_twist + M);              // [n+1]
+
+    const int tid = threadIdx.x;
+    const int g = tid / TPF;          // group == accumulator component handled in the forward phase
+    const int t = tid - g * TPF;
+    double2* mybuf = xbuf + (size_t)g * C::XB;
+    uint64_t* myacc = acc + (size_t)g * N;
+    auto sync = [] { __syncthreads(); };
+
+    for (int i = tid; i < M; i += C::THREADS) { s_tw[i] = a.tw[i]; s_twist[i] = a.twist[i]; }
+
+    for (uint32_t ct = blockIdx.x; ct < a.count; ct += gridDim.x) {
+        const uint64_t* in = a.in + (size_t)ct * (a.n + 1);
+        __syncthreads();
+        for (uint32_t i = tid; i <= a.n; i += C::THREADS) s_ahat[i] = mod_switch(in[i], LOGN + 1);
+        __syncthreads();
+        {   // acc = X^{-bhat} * (0, .., 0, LUT)
+            const uint64_t* lut = a.luts + (size_t)a.lut_index[ct] * N;
+            const uint32_t bhat = s_ahat[a.n];
+            for (int j = tid; j < G * N; j += C::THREADS) {
+                int comp = j / N, jj = j - comp * N;
+                uint64_t v = 0;
+                if (comp == K) {
+                    uint32_t idx = (jj + bhat) & (2 * N - 1);
+                    v = idx < N ? lut[idx] : (uint64_t)0 - lut[idx - N];
+                }
+                acc[j] = v;
+            }
+        }
+        __syncthreads();
+
+        for (uint32_t i = 0; i < a.n; i++) {
+            const uint32_t ahat = s_ahat[i];
+            if (ahat == 0) continue;                                   // CTA-uniform
+            const double2* key_i = a.bsk + (size_t)i * G * a.level * G * M;
+            double2 part[G][8];
+#pragma unroll
+            for (int c = 0; c < G; c++)
+#pragma unroll
+                for (int e = 0; e < 8; e++) part[c][e] = make_double2(0.0, 0.0);
+
+            for (int lvl = 0; lvl < a.level; lvl++) {
+                double2 x[8];
+                // pass-0 input: digit polynomial of X^ahat*acc_g - acc_g, twisted
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    const int jc = t + e * TPF;
+                    uint64_t d0, d1;
+                    {
+                        uint32_t s0 = (uint32_t)(jc - (int)ahat) & (2 * N - 1);
+                        uint64_t r0 = s0 < N ? myacc[s0] : (uint64_t)0 - myacc[s0 - N];
+                        d0 = r0 - myacc[jc];
+                        uint32_t s1 = (uint32_t)(jc + M - (int)ahat) & (2 * N - 1);
+                        uint64_t r1 = s1 < N ? myacc[s1] : (uint64_t)0 - myacc[s1 - N];
+                        d1 = r1 - myacc[jc + M];
+                    }
+                    double2 v = make_double2((double)decompose_digit(d0, a.base_log, a.level, lvl + 1),
+                                             (double)decompose_digit(d1, a.base_log, a.level, lvl + 1));
+                    x[e] = cmul(v, s_twist[jc]);
+                }
+                if (lvl > 0) __syncthreads();                          // previous level's last-pass reads are done
+                fft_forward_regs<LOGM>(x, t, mybuf, s_tw, sync);
+                // Fourier MAC with BSK_i rows (g, lvl, c)
+                const double2* krow = key_i + ((size_t)(g * a.level + lvl) * G) * M;
+#pragma unroll
+                for (int c = 0; c < G; c++) {
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        const double2 kv = __ldg(krow + (size_t)c * M + e * TPF + t);
+                        double re = part[c][e].x, im = part[c][e].y;
+                        re = fma(x[e].x, kv.x, re); re = fma(-x[e].y, kv.y, re);
+                        im = fma(x[e].x, kv.y, im); im = fma(x[e].y, kv.x, im);
+                        part[c][e] = make_double2(re, im);
+                    }
+                }
+            }
+            // exchange partial spectra: group g keeps component g, ships the others
+            __syncthreads();                                           // all forward reads of xbuf finished
+#pragma unroll
+            for (int c = 0; c < G; c++) {
+                if (c == g) continue;
+                const int slot = (g < c) ? g : g - 1;                  // position of sender g in receiver c's buffer
+                double2* dst = xbuf + (size_t)c * C::XB + (size_t)slot * M;
+#pragma unroll
+                for (int e = 0; e < 8; e++) dst[e * TPF + t] = part[c][e];
+            }
+            __syncthreads();
+            double2 x[8];
+            {   // F_g = sum over r ascending of partial_r (own partial from registers, the others from smem)
+#pragma unroll
+                for (int r = 0; r < G; r++) {
+                    const bool own = (r == g);
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        double2 v = part[r][e];
+                        if (!own) v = mybuf[(size_t)((r < g) ? r : r - 1) * M + e * TPF + t];
+                        x[e] = (r == 0) ? v : cadd(x[e], v);
+                    }
+                }
+            }
+            __syncthreads();                                           // exchange reads done before buffers are reused
+            fft_inverse_regs<LOGM>(x, t, mybuf, s_tw, sync);
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const int jc = t + e * TPF;
+                double2 r = cmulc(x[e], s_twist[jc]);
+                myacc[jc] += double_to_torus(r.x * (1.0 / M));
+                myacc[jc + M] += double_to_torus(r.y * (1.0 / M));
+            }
+            __syncthreads();
+        }
+
+        // sample extract coefficient 0 -> LWE under the big key
+        uint64_t* o = a.out + (size_t)ct * ((size_t)K * N + 1);
+        for (int j = tid; j < K * N; j += C::THREADS) {
+            int comp = j / N, tt = j - comp * N;
+            const uint64_t* ar = acc + (size_t)comp * N;
+            uint64_t v = (tt == 0) ? ar[0] : (uint64_t)0 - ar[N - tt];
+            if (a.mode == 0) o[j] = v; else o[j] -= v;
+        }
+        if (tid == 0) {
+            uint64_t bv = acc[(size_t)K * N];
+            if (a.mode == 0) o[(size_t)K * N] = bv; else o[(size_t)K * N] -= bv + a.body_const;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Plain transforms: one group of TPF threads per polynomial.  MODE 0: u64 (signed) input -> thread-major
+// Fourier layout (BSK conversion).  MODE 1: double input -> canonical order (test hook).
+// ---------------------------------------------------------------------------------------------------
+template <int LOGN, int MODE>
+__global__ void __launch_bounds__(1 << (LOGN - 4))
+fft_forward_kernel(const void* __restrict__ in, double2* __restrict__ out, const double2* __restrict__ twist,
+                   const double2* __restrict__ tw, size_t polys) {
+    constexpr int N = 1 << LOGN, M = N / 2, LOGM = LOGN - 1, TPF = M / 8;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* buf = reinterpret_cast<double2*>(smem_raw);
+    double2* s_tw = buf + M;
+    const int t = threadIdx.x;
+    for (int i = t; i < M; i += TPF) s_tw[i] = tw[i];
+    auto sync = [] { __syncthreads(); };
+    for (size_t p = blockIdx.x; p < polys; p += gridDim.x) {
+        __syncthreads();
+        double2 x[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int jc = t + e * TPF;
+            double2 v;
+            if (MODE == 0) {
+                const uint64_t* src = reinterpret_cast<const uint64_t*>(in) + p * N;
+                v = make_double2((double)(int64_t)src[jc], (double)(int64_t)src[jc + M]);
+            } else {
+                const double* src = reinterpret_cast<const double*>(in) + p * N;
+                v = make_double2(src[jc], src[jc + M]);
+            }
+            x[e] = cmul(v, twist[jc]);
+        }
+        fft_forward_regs<LOGM>(x, t, buf, s_tw, sync);
+        double2* dst = out + p * M;
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            if (MODE == 0) dst[e * TPF + t] = x[e];
+            else dst[last_pass_index<LOGM>(t, e)] = x[e];
+        }
+    }
+}
+
+template <int LOGN>
+__global__ void __launch_bounds__(1 << (LOGN - 4))
+fft_inverse_kernel(const double2* __restrict__ in, uint64_t* __restrict__ out, const double2* __restrict__ twist,
+                   const double2* __restrict__ tw, size_t polys) {
+    constexpr int N = 1 << LOGN, M = N / 2, LOGM = LOGN - 1, TPF = M / 8;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* buf = reinterpret_cast<double2*>(smem_raw);
+    double2* s_tw = buf + M;
+    const int t = threadIdx.x;
+    for (int i = t; i < M; i += TPF) s_tw[i] = tw[i];
+    auto sync = [] { __syncthreads(); };
+    for (size_t p = blockIdx.x; p < polys; p += gridDim.x) {
+        __syncthreads();
+        double2 x[8];
+        const double2* src = in + p * M;
+#pragma unroll
+        for (int e = 0; e < 8; e++) x[e] = src[last_pass_index<LOGM>(t, e)];
+        fft_inverse_regs<LOGM>(x, t, buf, s_tw, sync);
+        uint64_t* dst = out + p * N;
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int jc = t + e * TPF;
+            double2 r = cmulc(x[e], twist[jc]);
+            dst[jc] = double_to_torus(r.x * (1.0 / M));
+            dst[jc + M] = double_to_torus(r.y * (1.0 / M));
+        }
+    }
+}
+
+// thread-major <-> canonical permutation of one Fourier polynomial (export / import of the BSK)
+template <int LOGN>
+__global__ void bsk_permute_kernel(const double2* __restrict__ in, double2* __restrict__ out, size_t polys, int to_canonical) {
+    constexpr int M = 1 << (LOGN - 1), LOGM = LOGN - 1, TPF = M / 8;
+    size_t total = polys * M;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t p = i / M; int r = (int)(i - p * M);
+        int e = r / TPF, t = r - e * TPF;
+        int canon = last_pass_index<LOGM>(t, e);
+        if (to_canonical) out[p * M + canon] = in[i]; else out[i] = in[p * M + canon];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host-side dispatch
+// ---------------------------------------------------------------------------------------------------
+template <int LOGN, int K>
+static int launch_pbs_t(const PbsArgs& a, int sm_count, cudaStream_t stream) {
+    using C = PbsCfg<LOGN, K>;
+    size_t smem = C::smem_bytes((int)a.n);
+    static bool configured = false;
+    static int blocks_per_sm = 1;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(pbs_kernel<LOGN, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(pbs)");
+        configured = true;
+    }
+    if (smem > 227 * 1024) return set_error(TFX_ERR_UNSUPPORTED, "pbs: shared memory footprint exceeds 227 KB");
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, pbs_kernel<LOGN, K>, C::THREADS, smem);
+    if (e != cudaSuccess) return set_cuda_error(e, "occupancy(pbs)");
+    if (blocks_per_sm < 1) return set_error(TFX_ERR_UNSUPPORTED, "pbs: kernel does not fit on an SM");
+    unsigned grid = (unsigned)sm_count * blocks_per_sm;
+    if (grid > a.count) grid = a.count;
+    pbs_kernel<LOGN, K><<<grid, C::THREADS, smem, stream>>>(a);
+    count_launch();
+    return check_launch("pbs_kernel");
+}
+
+int pbs_supported(uint32_t N, uint32_t k) {
+    if (k == 1) return N == 512 || N == 1024 || N == 2048 || N == 4096;
+    if (k == 2) return N == 512 || N == 1024 || N == 2048;
+    return 0;
+}
+
+int launch_pbs(const PbsLaunch& p, cudaStream_t stream) {
+    PbsArgs a;
+    a.bsk = reinterpret_cast<const double2*>(p.bsk); a.twist = reinterpret_cast<const double2*>(p.twist);
+    a.tw = reinterpret_cast<const double2*>(p.tw);
+    a.in = p.in; a.luts = p.luts; a.lut_index = p.lut_index; a.out = p.out;
+    a.n = p.n; a.base_log = p.base_log; a.level = p.level; a.mode = p.mode; a.body_const = p.body_const;
+    a.count = (uint32_t)p.count;
+#define TFX_PBS_CASE(LN, KK) if (p.N == (1u << LN) && p.k == KK) return launch_pbs_t<LN, KK>(a, p.sm_count, stream);
+    TFX_PBS_CASE(9, 1) TFX_PBS_CASE(10, 1) TFX_PBS_CASE(11, 1) TFX_PBS_CASE(12, 1)
+    TFX_PBS_CASE(9, 2) TFX_PBS_CASE(10, 2) TFX_PBS_CASE(11, 2)
+#undef TFX_PBS_CASE
+    return set_error(TFX_ERR_UNSUPPORTED, "pbs: no kernel compiled for this (N, k)");
+}
+
+template <int LOGN>
+static int launch_fft_t(int which, const void* in, void* out, const double* twist, const double* tw, size_t polys,
+                        int sm_count, cudaStream_t stream) {
+    constexpr int M = 1 << (LOGN - 1), TPF = M / 8;
+    size_t smem = (size_t)M * 16 * 2;
+    unsigned grid = (unsigned)(polys < (size_t)sm_count * 8 ? polys : (size_t)sm_count * 8);
+    if (grid == 0) return TFX_OK;
+    const double2* tws = reinterpret_cast<const double2*>(twist);
+    const double2* twd = reinterpret_cast<const double2*>(tw);
+    cudaError_t e;
+    if (which == 0) {
+        e = cudaFuncSetAttribute(fft_forward_kernel<LOGN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_cuda_error(e, "attr");
+        fft_forward_kernel<LOGN, 0><<<grid, TPF, smem, stream>>>(in, reinterpret_cast<double2*>(out), tws, twd, polys);
+    } else if (which == 1) {
+        e = cudaFuncSetAttribute(fft_forward_kernel<LOGN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_cuda_error(e, "attr");
+        fft_forward_kernel<LOGN, 1><<<grid, TPF, smem, stream>>>(in, reinterpret_cast<double2*>(out), tws, twd, polys);
+    } else if (which == 2) {
+        e = cudaFuncSetAttribute(fft_inverse_kernel<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_cuda_error(e, "attr");
+        fft_inverse_kernel<LOGN><<<grid, TPF, smem, stream>>>(reinterpret_cast<const double2*>(in),
+                                                                reinterpret_cast<uint64_t*>(out), tws, twd, polys);
+    } else {
+        bsk_permute_kernel<LOGN><<<(unsigned)sm_count * 4, 256, 0, stream>>>(
+            reinterpret_cast<const double2*>(in), reinterpret_cast<double2*>(out), polys, which == 3 ? 1 : 0);
+    }
+    count_launch();
+    return check_launch("fft kernel");
+}
+
+// which: 0 = u64 -> thread-major Fourier, 1 = double -> canonical Fourier, 2 = canonical Fourier -> torus,
+//        3 = thread-major -> canonical, 4 = canonical -> thread-major
+int launch_fft(int which, uint32_t N, const void* in, void* out, const double* twist, const double* tw, size_t polys,
+               int sm_count, cudaStream_t stream) {
+    switch (N) {
+        case 512:  return launch_fft_t<9>(which, in, out, twist, tw, polys, sm_count, stream);
+        case 1024: return launch_fft_t<10>(which, in, out, twist, tw, polys, sm_count, stream);
+        case 2048: return launch_fft_t<11>(which, in, out, twist, tw, polys, sm_count, stream);
+        case 4096: return launch_fft_t<12>(which, in, out, twist, tw, polys, sm_count, stream);
+        default: return set_error(TFX_ERR_UNSUPPORTED, "fft: unsupported N");
+    }
+}
+
+}  // namespace tfx

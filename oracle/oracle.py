@@ -188,17 +188,17 @@ def pbs(bsk_f, base_log, cts, luts, lut_index, mode=0, body_const=0, out=None) -
     return out
 
 
-def conv2d(x, w, stride=1, pad=0, bias_pt=None) -> np.ndarray:
+def conv2d(x, w, stride=1, pad=0, bias_pt=None, depthwise=False) -> np.ndarray:
     x = np.ascontiguousarray(x, dtype=np.uint64)
     Cin, H, W, words = x.shape
     w = np.ascontiguousarray(w, dtype=np.int32)
     Cout, Cin2, kh, kw = w.shape
-    assert Cin2 == Cin
+    assert Cin2 == (1 if depthwise else Cin)
     Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
     out = np.empty((Cout, Ho, Wo, words), dtype=np.uint64)
     bp = None if bias_pt is None else np.ascontiguousarray(bias_pt, dtype=np.uint64)
     lib().orc_conv2d(_p(x), C.c_uint32(Cin), C.c_uint32(H), C.c_uint32(W), C.c_uint32(words), _p(w), C.c_uint32(Cout),
-                     C.c_uint32(kh), C.c_uint32(kw), C.c_uint32(stride), C.c_uint32(pad), _p(bp), _p(out))
+                     C.c_uint32(kh), C.c_uint32(kw), C.c_uint32(stride), C.c_uint32(pad), _p(bp), C.c_uint32(int(depthwise)), _p(out))
     return out
 
 

@@ -540,11 +540,12 @@ ORC_API void orc_pbs(const double* bsk_f, uint32_t n, uint32_t k, uint32_t N, in
 /* ------------------------------------------------------------------------------------------------
  * 9. Leveled ops on big-key ciphertext tensors: integer-weight conv2d, add, scalar ops.
  *    in  u64 [Cin][H][W][dim+1] ; w int32 [Cout][Cin][kh][kw] ; out u64 [Cout][Ho][Wo][dim+1]
- *    bias_pt (optional, u64 [Cout]) is added to the body word.
+ *    bias_pt (optional, u64 [Cout]) is added to the body word.  depthwise: w is [Cout][1][kh][kw], ic = oc.
  * ---------------------------------------------------------------------------------------------- */
 ORC_API void orc_conv2d(const uint64_t* in, uint32_t Cin, uint32_t H, uint32_t W, uint32_t words,
                         const int32_t* w, uint32_t Cout, uint32_t kh, uint32_t kw, uint32_t stride, uint32_t pad,
-                        const uint64_t* bias_pt, uint64_t* out) {
+                        const uint64_t* bias_pt, uint32_t depthwise, uint64_t* out) {
+    uint32_t Cin_eff = depthwise ? 1 : Cin;
     uint32_t Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
 #pragma omp parallel for schedule(dynamic, 1) collapse(2)
     for (int64_t oc = 0; oc < (int64_t)Cout; oc++)
@@ -552,12 +553,13 @@ ORC_API void orc_conv2d(const uint64_t* in, uint32_t Cin, uint32_t H, uint32_t W
             for (uint32_t ox = 0; ox < Wo; ox++) {
                 uint64_t* o = out + (((uint64_t)oc * Ho + oy) * Wo + ox) * words;
                 memset(o, 0, 8ULL * words);
-                for (uint32_t ic = 0; ic < Cin; ic++)
+                for (uint32_t icw = 0; icw < Cin_eff; icw++)
                     for (uint32_t ky = 0; ky < kh; ky++)
                         for (uint32_t kx = 0; kx < kw; kx++) {
                             int64_t iy = (int64_t)oy * stride + ky - pad, ix = (int64_t)ox * stride + kx - pad;
                             if (iy < 0 || iy >= (int64_t)H || ix < 0 || ix >= (int64_t)W) continue;
-                            int32_t wv = w[((oc * Cin + ic) * kh + ky) * kw + kx];
+                            uint32_t ic = depthwise ? (uint32_t)oc : icw;
+                            int32_t wv = w[((oc * Cin_eff + icw) * kh + ky) * kw + kx];
                             if (!wv) continue;
                             const uint64_t* src = in + (((uint64_t)ic * H + iy) * W + ix) * words;
                             uint64_t wu = (uint64_t)(int64_t)wv;

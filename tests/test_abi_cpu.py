@@ -1,0 +1,53 @@
+"""CPU-side checks of the C-ABI library: it loads without a GPU, exports every symbol include/tfx.h declares,
+fails loudly (no CPU fallback) when asked to compute, and its FFT tables equal the oracle's."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tfx_b200 import binding
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = binding.load_library()
+    header = open(os.path.join(ROOT, "include", "tfx.h")).read()
+    declared = set(re.findall(r"\b(tfx_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/tfx.h but not exported"
+    assert declared == set(binding.SYMBOLS), "binding.SYMBOLS out of sync with include/tfx.h"
+    assert b"sm_100a" in lib.tfx_version()
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = binding.load_library()
+    h = C.c_void_p()
+    rc = lib.tfx_ctx_create(0, None, 0, C.byref(h))
+    assert rc != 0 and b"no CPU fallback" in lib.tfx_last_error()
+    with pytest.raises(binding.TfxError):
+        binding.Context(0)
+
+
+def test_fft_tables_equal_oracle(oracle):
+    for N in (512, 1024, 2048, 4096):
+        twist, tw = binding.fft_tables(N)
+        o_twist, o_tw = oracle.fft_tables(N)
+        assert np.array_equal(twist, o_twist)
+        assert np.array_equal(tw, o_tw)
+        # exact special values the kernels rely on
+        M = N // 2
+        assert twist[0, 0] == 1.0 and twist[0, 1] == 0.0
+        assert tw[M - 4, 0] == 1.0 and tw[M - 3, 0] == 0.0 and tw[M - 3, 1] == 1.0      # half = 2 stage: 1, i
+
+
+def test_pbs_supported_matrix():
+    lib = binding.load_library()
+    assert lib.tfx_pbs_supported(4096, 1) == 1 and lib.tfx_pbs_supported(2048, 2) == 1
+    assert lib.tfx_pbs_supported(4096, 3) == 0 and lib.tfx_pbs_supported(100, 1) == 0
