@@ -1,0 +1,514 @@
+"""Integer circuit IR + the compile front-end that builds it from a torch module.
+
+This is our realisation of what the reference obtains from Concrete-ML's compile_torch_model /
+compile_brevitas_qat_model (reference homomorphic_eval.py:276-295; intent summarised in SURVEY.md A.8):
+  * the input is quantised in the clear to n_bits (symmetric);
+  * every Conv2d becomes an integer conv with clear integer weights, the residual add and the average pool are
+    leveled integer ops;
+  * everything univariate between two integer tensors (BatchNorm, ReLU, quantisers, the 1/k^2 of the pool,
+    re-quantisation) is fused into ONE per-channel table, evaluated after exact rounding of the accumulator to
+    rounding_threshold_bits;
+  * accumulator widths come from the calibration set (like Concrete's inputset-driven bit-width assignment).
+The IR is plain data (numpy arrays + ints) so that the CUDA executor (executor.py), the clear integer evaluator
+below and the CPU oracle's evaluator (oracle/circuit_oracle.py, test infrastructure) all run the same circuit.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.fx as fx
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .params import CircuitNoiseSpec, RoundedLookup
+
+
+# --------------------------------------------------------------------------------------------------------
+# IR
+# --------------------------------------------------------------------------------------------------------
+@dataclass
+class QuantInfo:
+    scale: float
+    qmin: int
+    qmax: int
+
+
+@dataclass
+class ConvOp:
+    name: str
+    src: int
+    dst: int
+    weight: np.ndarray          # int32 [Cout][Cin or 1][kh][kw], already multiplied by 2^lshift
+    stride: int
+    pad: int
+    depthwise: bool
+    in_shape: Tuple[int, int, int]
+    out_shape: Tuple[int, int, int]
+    acc_bits: int = 0           # w
+    offset: int = 0             # added so the accumulator is unsigned: u = acc + offset in [0, 2^w)
+    lshift: int = 0
+    raw_weight: Optional[np.ndarray] = None   # before the encoding shift
+    kind: str = "conv"
+
+
+@dataclass
+class AddOp:
+    name: str
+    a: int
+    b: int
+    dst: int
+    shape: Tuple[int, int, int]
+    acc_bits: int = 0
+    offset: int = 0
+    sa: int = 1                 # 2^lshift of operand a
+    sb: int = 1
+    kind: str = "add"
+
+
+@dataclass
+class TluOp:
+    name: str
+    src: int                    # accumulator value (output of a conv / add)
+    dst: int
+    shape: Tuple[int, int, int]
+    acc_bits: int               # w
+    keep_bits: int              # t' = min(w, rounding bits)
+    tables: np.ndarray          # int64 [C][2^keep_bits] integer outputs q
+    out: QuantInfo
+    out_width: int = 0          # encoding width of the produced ciphertexts (delta = 2^(63 - out_width))
+    kind: str = "tlu"
+
+    @property
+    def lsbs(self) -> int:
+        return self.acc_bits - self.keep_bits
+
+
+@dataclass
+class Circuit:
+    input_shape: Tuple[int, int, int]
+    input_quant: QuantInfo
+    input_id: int
+    input_width: int
+    ops: List[object]
+    output_id: int
+    output_shape: Tuple[int, ...]
+    output_is_acc: bool         # True: decrypt an accumulator (offset/width below); False: a TLU output
+    output_width: int
+    output_offset: int
+    output_scale: float         # real value = output_scale * integer
+    n_bits: int
+    rounding_bits: int
+    p_error: float
+
+    # ---- statistics ------------------------------------------------------------------------------------
+    def lookups(self) -> List[TluOp]:
+        return [op for op in self.ops if op.kind == "tlu"]
+
+    def pbs_count(self) -> Dict[str, int]:
+        tlu = sum(int(np.prod(op.shape)) for op in self.lookups())
+        bit = sum(int(np.prod(op.shape)) * op.lsbs for op in self.lookups())
+        return {"tlu": tlu, "bit": bit, "total": tlu + bit}
+
+    def macs(self) -> int:
+        total = 0
+        for op in self.ops:
+            if op.kind == "conv":
+                cout, ho, wo = op.out_shape
+                total += cout * ho * wo * int(np.prod(op.weight.shape[1:]))
+        return total
+
+    def maximum_integer_bit_width(self) -> int:
+        widths = [op.acc_bits for op in self.ops if op.kind in ("conv", "add")]
+        return max(widths + [self.input_width])
+
+    def noise_spec(self, input_std: float = 2.0 ** -50) -> CircuitNoiseSpec:
+        producers = {op.dst: op for op in self.ops}
+        looks = []
+        for op in self.lookups():
+            lin = producers[op.src]
+            if lin.kind == "conv":
+                w = lin.weight.astype(np.float64)
+                norm2 = float((w.reshape(w.shape[0], -1) ** 2).sum(axis=1).max())
+                fresh = lin.src == self.input_id
+            else:
+                norm2 = float(lin.sa ** 2 + lin.sb ** 2)
+                fresh = False
+            looks.append(RoundedLookup(op.acc_bits, op.keep_bits, max(norm2, 1.0), fresh, int(np.prod(op.shape))))
+        return CircuitNoiseSpec(looks, self.p_error, input_std)
+
+    def to_text(self) -> str:
+        """Printable listing (plays the role of fhe_circuit.mlir, reference homomorphic_eval.py:311)."""
+        lines = [f"circuit(input %{self.input_id}: eint<{self.input_width}>[{','.join(map(str, self.input_shape))}], "
+                 f"n_bits={self.n_bits}, rounding={self.rounding_bits}, p_error={self.p_error})"]
+        for op in self.ops:
+            if op.kind == "conv":
+                k = "sum_pool" if op.depthwise else "conv2d"
+                lines.append(f"  %{op.dst} = {k}(%{op.src}) {{weight=i32{list(op.weight.shape)}, stride={op.stride}, pad={op.pad}, "
+                             f"lshift={op.lshift}, offset={op.offset}}} : eint<{op.acc_bits}>{list(op.out_shape)}   // {op.name}")
+            elif op.kind == "add":
+                lines.append(f"  %{op.dst} = add(%{op.a} * {op.sa}, %{op.b} * {op.sb}) {{offset={op.offset}}} : eint<{op.acc_bits}>{list(op.shape)}   // {op.name}")
+            else:
+                lines.append(f"  %{op.dst} = round_lsbs<{op.lsbs}>.table_lookup(%{op.src}) {{tables=i64{list(op.tables.shape)}}} : "
+                             f"eint<{op.out_width}>{list(op.shape)}   // {op.name}")
+        lines.append(f"  return %{self.output_id}")
+        return "\n".join(lines)
+
+
+# --------------------------------------------------------------------------------------------------------
+# Clear integer evaluator (exact semantics of the circuit; also the noise-free model behind fhe='simulate')
+# --------------------------------------------------------------------------------------------------------
+def _int_conv(x: np.ndarray, op: ConvOp, weight: np.ndarray) -> np.ndarray:
+    """x: int64 [B][C][H][W] -> int64; float64 conv is exact for these magnitudes (< 2^53)."""
+    xt = torch.from_numpy(x.astype(np.float64))
+    wt = torch.from_numpy(weight.astype(np.float64))
+    groups = x.shape[1] if op.depthwise else 1
+    y = F.conv2d(xt, wt, stride=op.stride, padding=op.pad, groups=groups)
+    return np.rint(y.numpy()).astype(np.int64)
+
+
+def quantize_input(circ: Circuit, x: np.ndarray) -> np.ndarray:
+    q = np.rint(np.asarray(x, dtype=np.float64) / circ.input_quant.scale)
+    return np.clip(q, circ.input_quant.qmin, circ.input_quant.qmax).astype(np.int64)
+
+
+def tlu_apply(op: TluOp, offset: int, acc: np.ndarray) -> np.ndarray:
+    """acc int64 [B][C][H][W] (true accumulator, before offset) -> q int64; models the padding-bit wrap."""
+    w, lsbs, t = op.acc_bits, op.lsbs, op.keep_bits
+    half = (1 << (lsbs - 1)) if lsbs > 0 else 0
+    u = (acc + offset + half) & ((1 << (w + 1)) - 1)
+    idx = u >> lsbs                                  # in [0, 2^(t+1))
+    neg = idx >= (1 << t)
+    idx = idx & ((1 << t) - 1)
+    C = op.tables.shape[0]
+    ch = np.arange(C).reshape(1, C, 1, 1)
+    q = op.tables[np.broadcast_to(ch, idx.shape), idx]
+    return np.where(neg, -q, q)
+
+
+def evaluate_clear(circ: Circuit, q_in: np.ndarray, collect: Optional[dict] = None) -> np.ndarray:
+    """q_in int64 [B][C][H][W] -> integer outputs [B][...] (accumulator or table outputs)."""
+    vals = {circ.input_id: q_in.astype(np.int64)}
+    offs = {}
+    for op in circ.ops:
+        if op.kind == "conv":
+            vals[op.dst] = _int_conv(vals[op.src], op, op.raw_weight if op.raw_weight is not None else op.weight)
+            offs[op.dst] = op.offset
+        elif op.kind == "add":
+            vals[op.dst] = vals[op.a] + vals[op.b]
+            offs[op.dst] = op.offset
+        else:
+            vals[op.dst] = tlu_apply(op, offs[op.src], vals[op.src])
+        if collect is not None:
+            collect[op.dst] = vals[op.dst]
+    out = vals[circ.output_id]
+    return out.reshape(out.shape[0], *circ.output_shape)
+
+
+def dequantize_output(circ: Circuit, q_out: np.ndarray) -> np.ndarray:
+    return q_out.astype(np.float64) * circ.output_scale
+
+
+# --------------------------------------------------------------------------------------------------------
+# Front-end
+# --------------------------------------------------------------------------------------------------------
+class _Tracer(fx.Tracer):
+    """Quant* modules (Brevitas or the stubs) and standard layers are leaves."""
+
+    def is_leaf_module(self, m: nn.Module, qualname: str) -> bool:
+        if type(m).__name__.startswith("Quant"):
+            return True
+        return super().is_leaf_module(m, qualname)
+
+
+@dataclass
+class _Sym:
+    """a float tensor = chain(scale * integer accumulator) not yet turned into a table"""
+    lin: int                                  # value id of the integer tensor underneath
+    lin_is_acc: bool                          # True: conv/add output; False: a quantised tensor (input / table output)
+    scale: float                              # real = scale * int (before the chain)
+    chain: List[Callable[[torch.Tensor], torch.Tensor]]
+    shape: Tuple[int, ...]
+    affine_only: bool = True                  # chain is a pure positive scaling (can be decoded without a table)
+    affine_factor: float = 1.0
+
+
+def _bits_for_range(lo: int, hi: int) -> int:
+    span = hi - lo + 1
+    return max(1, int(math.ceil(math.log2(span)))) if span > 1 else 1
+
+
+def _weight_bits(mod: nn.Module, n_bits: int) -> int:
+    for attr in ("weight_bit_width", "bit_width"):
+        v = getattr(mod, attr, None)
+        if isinstance(v, int):
+            return v
+    return n_bits
+
+
+def _act_bits(mod: nn.Module, n_bits: int) -> int:
+    v = getattr(mod, "act_bit_width", None)
+    return v if isinstance(v, int) else n_bits
+
+
+class CircuitBuilder:
+    def __init__(self, model: nn.Module, calib: torch.Tensor, n_bits: int = 5, rounding_threshold_bits: int = 6,
+                 p_error: float = 0.01, range_margin: float = 0.0):
+        self.model = model.eval()
+        self.n_bits, self.t, self.p_error, self.margin = n_bits, rounding_threshold_bits, p_error, range_margin
+        self.calib = calib.detach().to(torch.float64).cpu()
+        self.ops: List[object] = []
+        self.next_id = 0
+        self.ints: Dict[int, np.ndarray] = {}          # calibration integers per value id
+        self.qinfo: Dict[int, QuantInfo] = {}          # for quantised tensors
+        self.acc_of: Dict[int, object] = {}            # value id -> producing linear op
+        self.materialized: Dict[int, int] = {}         # fx node id -> quantised value id
+        self.consumers: Dict[int, List[Tuple[object, str]]] = {}
+
+    def _new(self) -> int:
+        self.next_id += 1
+        return self.next_id - 1
+
+    # ---- accumulator range / width -----------------------------------------------------------------------
+    def _finish_acc(self, op, acc: np.ndarray):
+        lo, hi = int(acc.min()), int(acc.max())
+        if self.margin > 0:
+            m = int(math.ceil(self.margin * max(1, hi - lo)))
+            lo, hi = lo - m, hi + m
+        # choose w so that the rounded index still fits: hi - lo + half < 2^w
+        w = _bits_for_range(lo, hi)
+        while w > self.t and (hi - lo) + (1 << (w - self.t - 1)) >= (1 << w):
+            w += 1
+        op.acc_bits, op.offset = w, -lo
+
+    # ---- table construction ------------------------------------------------------------------------------
+    def _materialize(self, node_key, sym: _Sym, forced_scale: Optional[float] = None, out_bits: Optional[int] = None) -> int:
+        if node_key in self.materialized:
+            vid = self.materialized[node_key]
+            if forced_scale is not None and abs(self.qinfo[vid].scale - forced_scale) > 1e-12 * forced_scale:
+                raise NotImplementedError("residual add of two already-quantised tensors with different scales")
+            return vid
+        if not sym.lin_is_acc:
+            if sym.chain:
+                raise NotImplementedError("univariate op directly on a quantised tensor without a linear op in between")
+            self.materialized[node_key] = sym.lin
+            return sym.lin
+        lin_op = self.acc_of[sym.lin]
+        acc = self.ints[sym.lin]                                             # [B][C][H][W]
+        w, off = lin_op.acc_bits, lin_op.offset
+        keep = min(w, self.t)
+        lsbs = w - keep
+        C = acc.shape[1]
+        # float function per channel on every representable rounded accumulator value
+        idx = np.arange(1 << keep, dtype=np.int64)
+        acc_vals = (idx << lsbs) - off                                       # value the index stands for
+        xin = torch.from_numpy(np.broadcast_to(acc_vals.reshape(1, 1, -1, 1), (1, C, 1 << keep, 1)).astype(np.float64) * sym.scale)
+        y = xin
+        for fn in sym.chain:
+            y = fn(y)
+        y = y.reshape(C, 1 << keep).numpy()
+        # output quantiser: calibrate on the values the calibration set actually reaches
+        half = (1 << (lsbs - 1)) if lsbs > 0 else 0
+        cal_idx = np.clip((acc + off + half) >> lsbs, 0, (1 << keep) - 1)
+        ch = np.arange(C).reshape(1, C, 1, 1)
+        y_cal = y[np.broadcast_to(ch, cal_idx.shape), cal_idx]
+        nb = out_bits if out_bits is not None else self.n_bits
+        signed = bool(y_cal.min() < 0)
+        qmax = (1 << (nb - 1)) - 1 if signed else (1 << nb) - 1
+        if forced_scale is None:
+            amax = float(np.abs(y_cal).max())
+            scale = (amax / qmax) if amax > 0 else 1.0
+            qlo, qhi = (-qmax if signed else 0), qmax
+        else:
+            scale = forced_scale
+            reach = int(math.ceil(float(np.abs(y_cal).max()) / scale)) + 1
+            qlo, qhi = (-reach if signed else 0), reach
+        tables = np.clip(np.rint(y / scale), qlo, qhi).astype(np.int64)
+        vid = self._new()
+        op = TluOp(f"tlu_{vid}", sym.lin, vid, tuple(acc.shape[1:]), w, keep, tables, QuantInfo(scale, qlo, qhi))
+        self.ops.append(op)
+        self.ints[vid] = tlu_apply(op, off, acc)
+        self.qinfo[vid] = op.out
+        self.materialized[node_key] = vid
+        return vid
+
+    # ---- graph walk -------------------------------------------------------------------------------------
+    def build(self) -> Circuit:
+        tracer = _Tracer()
+        graph = tracer.trace(self.model)
+        mods = dict(self.model.named_modules())
+        env: Dict[fx.Node, _Sym] = {}
+        out_sym = None
+        for node in graph.nodes:
+            if node.op == "placeholder":
+                x = self.calib
+                amax = float(x.abs().max())
+                qmax = (1 << (self.n_bits - 1)) - 1
+                scale = amax / qmax if amax > 0 else 1.0
+                vid = self._new()
+                self.input_id = vid
+                self.input_quant = QuantInfo(scale, -qmax, qmax)
+                self.ints[vid] = np.clip(np.rint(x.numpy() / scale), -qmax, qmax).astype(np.int64)
+                self.qinfo[vid] = self.input_quant
+                env[node] = _Sym(vid, False, scale, [], tuple(x.shape[1:]))
+            elif node.op == "call_module":
+                m = mods[node.target]
+                src = env[node.args[0]]
+                tname = type(m).__name__
+                if isinstance(m, nn.Conv2d) or tname == "QuantConv2d":
+                    env[node] = self._conv(node, m, src, node.args[0])
+                elif isinstance(m, nn.BatchNorm2d):
+                    env[node] = self._chain(src, _bn_fn(m), False)
+                elif isinstance(m, nn.ReLU) or tname == "QuantReLU":
+                    env[node] = self._chain(src, torch.relu, False)
+                elif tname == "QuantIdentity" or isinstance(m, (nn.Identity, nn.Dropout)):
+                    env[node] = src if not src.lin_is_acc else self._chain(src, _identity, src.affine_only, keep_affine=True)
+                elif isinstance(m, nn.AvgPool2d):
+                    env[node] = self._avgpool(node, m, src, node.args[0])
+                elif isinstance(m, nn.Flatten):
+                    env[node] = _Sym(src.lin, src.lin_is_acc, src.scale, src.chain, (int(np.prod(src.shape)),), src.affine_only, src.affine_factor)
+                else:
+                    raise NotImplementedError(f"unsupported module {tname} at {node.target}")
+            elif node.op == "call_function":
+                fname = getattr(node.target, "__name__", str(node.target))
+                if fname in ("add", "iadd"):
+                    env[node] = self._add(node, env[node.args[0]], env[node.args[1]], node.args[0], node.args[1])
+                elif fname == "relu":
+                    env[node] = self._chain(env[node.args[0]], torch.relu, False)
+                elif fname == "flatten":
+                    src = env[node.args[0]]
+                    env[node] = _Sym(src.lin, src.lin_is_acc, src.scale, src.chain, (int(np.prod(src.shape)),), src.affine_only, src.affine_factor)
+                else:
+                    raise NotImplementedError(f"unsupported function {fname}")
+            elif node.op == "output":
+                out_sym = env[node.args[0]]
+                out_key = node.args[0]
+            else:
+                raise NotImplementedError(f"unsupported fx node {node.op}")
+        return self._finish(out_sym, out_key)
+
+    def _chain(self, src: _Sym, fn, affine: bool, keep_affine: bool = False) -> _Sym:
+        if not src.lin_is_acc:
+            raise NotImplementedError("univariate op on a quantised tensor (needs a linear op first)")
+        return _Sym(src.lin, True, src.scale, src.chain + [fn], src.shape,
+                    src.affine_only and (affine or keep_affine), src.affine_factor)
+
+    def _register(self, vid: int, op, role: str):
+        self.consumers.setdefault(vid, []).append((op, role))
+
+    def _conv(self, node, m, src: _Sym, src_key) -> _Sym:
+        q = self._materialize(src_key, src)
+        wb = _weight_bits(m, self.n_bits)
+        wq_max = (1 << (wb - 1)) - 1
+        wf = m.weight.detach().to(torch.float64)
+        s_w = float(wf.abs().max()) / wq_max if float(wf.abs().max()) > 0 else 1.0
+        wq = torch.clamp(torch.round(wf / s_w), -wq_max, wq_max).numpy().astype(np.int32)
+        if m.bias is not None:
+            raise NotImplementedError("conv bias (the reference models use bias=False)")
+        stride = m.stride[0]; pad = m.padding[0]
+        cin, h, w_ = self.ints[q].shape[1:]
+        vid = self._new()
+        op = ConvOp(f"conv_{node.target}", q, vid, wq, stride, pad, False, (cin, h, w_), (0, 0, 0), raw_weight=wq.copy())
+        acc = _int_conv(self.ints[q], op, wq)
+        op.out_shape = tuple(acc.shape[1:])
+        self._finish_acc(op, acc)
+        self.ops.append(op)
+        self.ints[vid] = acc
+        self.acc_of[vid] = op
+        self._register(q, op, "src")
+        return _Sym(vid, True, self.qinfo[q].scale * s_w, [], op.out_shape)
+
+    def _avgpool(self, node, m, src: _Sym, src_key) -> _Sym:
+        q = self._materialize(src_key, src)
+        k = m.kernel_size if isinstance(m.kernel_size, int) else m.kernel_size[0]
+        s = m.stride if isinstance(m.stride, int) else m.stride[0]
+        c, h, w_ = self.ints[q].shape[1:]
+        wq = np.ones((c, 1, k, k), dtype=np.int32)
+        vid = self._new()
+        op = ConvOp(f"sumpool_{node.target}", q, vid, wq, s, 0, True, (c, h, w_), (0, 0, 0), raw_weight=wq.copy())
+        acc = _int_conv(self.ints[q], op, wq)
+        op.out_shape = tuple(acc.shape[1:])
+        self._finish_acc(op, acc)
+        self.ops.append(op)
+        self.ints[vid] = acc
+        self.acc_of[vid] = op
+        self._register(q, op, "src")
+        f = 1.0 / (k * k)
+        return _Sym(vid, True, self.qinfo[q].scale, [lambda y, f=f: y * f], op.out_shape, True, f)
+
+    def _add(self, node, a: _Sym, b: _Sym, ka, kb) -> _Sym:
+        # operands must share one scale: an already-quantised operand dictates it, otherwise the larger range does
+        qa = self.materialized.get(ka) if a.lin_is_acc else a.lin
+        qb = self.materialized.get(kb) if b.lin_is_acc else b.lin
+        if qa is not None and qb is None:
+            qb = self._materialize(kb, b, forced_scale=self.qinfo[qa].scale)
+        elif qb is not None and qa is None:
+            qa = self._materialize(ka, a, forced_scale=self.qinfo[qb].scale)
+        elif qa is None and qb is None:
+            qa = self._materialize(ka, a)
+            qb = self._materialize(kb, b, forced_scale=self.qinfo[qa].scale)
+        elif abs(self.qinfo[qa].scale - self.qinfo[qb].scale) > 1e-12 * self.qinfo[qa].scale:
+            raise NotImplementedError("residual add of two already-quantised tensors with different scales")
+        vid = self._new()
+        op = AddOp(f"add_{node.name}", qa, qb, vid, tuple(self.ints[qa].shape[1:]))
+        acc = self.ints[qa] + self.ints[qb]
+        self._finish_acc(op, acc)
+        self.ops.append(op)
+        self.ints[vid] = acc
+        self.acc_of[vid] = op
+        self._register(qa, op, "a")
+        self._register(qb, op, "b")
+        return _Sym(vid, True, self.qinfo[qa].scale, [], op.shape)
+
+    def _finish(self, out_sym: _Sym, out_key) -> Circuit:
+        if out_sym.lin_is_acc and out_sym.affine_only:
+            out_id, is_acc = out_sym.lin, True
+            lin = self.acc_of[out_id]
+            out_width, out_off = lin.acc_bits, lin.offset
+            out_scale = out_sym.scale * out_sym.affine_factor
+        else:
+            vid = self._materialize(out_key, out_sym) if out_sym.lin_is_acc else out_sym.lin
+            out_id, is_acc = vid, False
+            qi = self.qinfo[vid]
+            out_width = _bits_for_range(qi.qmin, qi.qmax) + 1
+            out_off, out_scale = 0, qi.scale
+        # encoding widths: a quantised tensor is emitted at the width of its widest consumer; narrower consumers shift
+        width_of: Dict[int, int] = {}
+        for vid, cons in self.consumers.items():
+            width_of[vid] = max(op.acc_bits for op, _ in cons)
+        for vid, cons in self.consumers.items():
+            for op, role in cons:
+                ls = width_of[vid] - op.acc_bits
+                if op.kind == "conv":
+                    op.lshift = ls
+                    op.weight = (op.raw_weight.astype(np.int64) << ls).astype(np.int32)
+                elif role == "a":
+                    op.sa = 1 << ls
+                else:
+                    op.sb = 1 << ls
+        for op in self.ops:
+            if op.kind == "tlu":
+                op.out_width = width_of.get(op.dst, out_width)
+        return Circuit(tuple(self.calib.shape[1:]), self.input_quant, self.input_id, width_of[self.input_id], self.ops, out_id,
+                       tuple(out_sym.shape), is_acc, out_width, out_off, out_scale, self.n_bits, self.t, self.p_error)
+
+
+def _identity(y):
+    return y
+
+
+def _bn_fn(m: nn.BatchNorm2d):
+    mean = m.running_mean.detach().to(torch.float64).reshape(1, -1, 1, 1)
+    var = m.running_var.detach().to(torch.float64).reshape(1, -1, 1, 1)
+    g = (m.weight.detach().to(torch.float64) if m.affine else torch.ones_like(m.running_mean, dtype=torch.float64)).reshape(1, -1, 1, 1)
+    b = (m.bias.detach().to(torch.float64) if m.affine else torch.zeros_like(m.running_mean, dtype=torch.float64)).reshape(1, -1, 1, 1)
+    inv = g / torch.sqrt(var + m.eps)
+    return lambda y: (y - mean) * inv + b
+
+
+def build_circuit(model: nn.Module, calib: torch.Tensor, n_bits: int = 5, rounding_threshold_bits: int = 6,
+                  p_error: float = 0.01, range_margin: float = 0.0) -> Circuit:
+    return CircuitBuilder(model, calib, n_bits, rounding_threshold_bits, p_error, range_margin).build()

@@ -1,0 +1,223 @@
+"""GPU executor of a Circuit: keygen, encrypt, run (leveled ops + rounding chains + table lookups), decrypt.
+
+The layer loop is host Python; every arithmetic step is a call into libtfx_b200.so on the context's stream
+(binding.py).  Replaces what Circuit.keygen / encrypt_run_decrypt do behind reference homomorphic_eval.py:315,:70.
+
+Multi-GPU: keys are replicated (every rank generates the same keys from the same seed, no
+broadcast needed), each table-lookup layer is partitioned by output channel over the ranks — a rank computes the
+leveled op, the rounding chain and the PBS only for its own channels — and the layer output is re-assembled with
+an all-gather over NCCL.
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .binding import Context, KeySet, PbsParams, launch_count
+from .circuit import Circuit, ConvOp, AddOp, TluOp
+
+MASK64 = (1 << 64) - 1
+TLU_SET, BIT_SET = 0, 1
+
+
+def lut_polynomials(tables: np.ndarray, keep_bits: int, N: int, out_width: int) -> np.ndarray:
+    """tables int64 [C][2^p] -> torus LUT polynomials u64 [C][N]: every entry repeated N/2^p times,
+    rotated by half a box; the top half-box holds -T[0] (negacyclic wrap).  Output delta = 2^(63 - out_width)."""
+    C, size = tables.shape
+    assert size == 1 << keep_bits and N % size == 0
+    box = N // size
+    j = np.arange(N)
+    slot = (j + box // 2) // box                      # 0 .. 2^p
+    delta = np.uint64(1) << np.uint64(63 - out_width)
+    vals = tables.astype(np.int64).view(np.uint64) * delta          # two's complement wrap is the torus encoding
+    lut = vals[:, slot % size]
+    wrap = slot >= size
+    lut[:, wrap] = (np.uint64(0) - vals[:, 0:1]).repeat(int(wrap.sum()), axis=1)
+    return np.ascontiguousarray(lut)
+
+
+def bit_lut(acc_bits: int, b: int, N: int) -> Tuple[np.ndarray, int]:
+    """constant LUT -c with c = 2^(62 - w + b): PBS gives -c / +c, adding c gives bit_b * 2^(63 - w + b)"""
+    c = 1 << (62 - acc_bits + b)
+    return np.full(N, (-c) & MASK64, dtype=np.uint64), c
+
+
+@dataclass
+class RunStats:
+    seconds: float = 0.0
+    pbs_tlu: int = 0
+    pbs_bit: int = 0
+    keyswitches: int = 0
+    launches: int = 0
+    layer_seconds: Optional[List[Tuple[str, float]]] = None
+
+
+class CircuitExecutor:
+    def __init__(self, circuit: Circuit, params: Tuple[PbsParams, PbsParams], ctx: Optional[Context] = None,
+                 rank: int = 0, world_size: int = 1, process_group=None, input_std: Optional[float] = None):
+        self.circ = circuit
+        self.params = list(params)
+        self.ctx = ctx if ctx is not None else Context(torch.cuda.current_device())
+        self.rank, self.world = rank, world_size
+        self.pg = process_group
+        self.big_dim = params[0].big_dim
+        self.words = self.big_dim + 1
+        self.input_std = input_std if input_std is not None else params[0].glwe_std
+        self.keys: Optional[KeySet] = None
+        self._luts: Dict[int, torch.Tensor] = {}
+        self._lut_index: Dict[int, torch.Tensor] = {}
+        self._bit_luts: Dict[Tuple[int, int], Tuple[torch.Tensor, int]] = {}
+        self._weights: Dict[int, torch.Tensor] = {}
+        self._bias: Dict[int, torch.Tensor] = {}
+        self._prepare_constants()
+
+    # ---- constants ------------------------------------------------------------------------------------------
+    def _prepare_constants(self):
+        dev = self.ctx.device
+        N_tlu, N_bit = self.params[TLU_SET].N, self.params[BIT_SET].N
+        for op in self.circ.ops:
+            if op.kind == "conv":
+                self._weights[op.dst] = torch.from_numpy(np.ascontiguousarray(op.weight)).to(dev)
+                half = (1 << (self._lsbs_after(op) - 1)) if self._lsbs_after(op) > 0 else 0
+                bias = ((op.offset + half) << (63 - op.acc_bits)) & MASK64
+                self._bias[op.dst] = self.ctx.to_device_u64(np.full(op.out_shape[0], bias, dtype=np.uint64))
+            elif op.kind == "tlu":
+                luts = lut_polynomials(op.tables, op.keep_bits, N_tlu, op.out_width)
+                self._luts[op.dst] = self.ctx.to_device_u64(luts)
+                C, H, W = op.shape
+                idx = np.repeat(np.arange(C, dtype=np.int32), H * W)
+                self._lut_index[op.dst] = torch.from_numpy(idx).to(dev)
+                for b in range(op.lsbs):
+                    key = (op.acc_bits, b)
+                    if key not in self._bit_luts:
+                        lut, c = bit_lut(op.acc_bits, b, N_bit)
+                        self._bit_luts[key] = (self.ctx.to_device_u64(lut[None]), c)
+        self._zero_idx = torch.zeros(max(int(np.prod(op.shape)) for op in self.circ.lookups()), dtype=torch.int32, device=dev)
+
+    def _lsbs_after(self, lin_op) -> int:
+        """rounding bits removed by the lookup that consumes this accumulator (0 if it is the circuit output)"""
+        for op in self.circ.ops:
+            if op.kind == "tlu" and op.src == lin_op.dst:
+                return op.lsbs
+        return 0
+
+    # ---- keys ------------------------------------------------------------------------------------------------
+    def keygen(self, seed=1, keep_standard_bsk: bool = False) -> float:
+        t0 = time.time()
+        if self.keys is not None:
+            self.keys.close()
+        self.keys = KeySet.generate(self.ctx, self.params, seed, keep_standard_bsk)
+        self.ctx.synchronize()
+        return time.time() - t0
+
+    def use_keys(self, keys: KeySet):
+        self.keys = keys
+
+    # ---- client side -------------------------------------------------------------------------------------------
+    def encrypt(self, q_in: np.ndarray, enc_seed=2) -> torch.Tensor:
+        """q_in int64 [C][H][W] -> ciphertexts int64-view u64 [C*H*W][big_dim+1] at the input encoding width"""
+        delta_shift = 63 - self.circ.input_width
+        pts = (q_in.astype(np.int64).reshape(-1).view(np.uint64) << np.uint64(delta_shift))
+        d_pts = self.ctx.to_device_u64(pts)
+        return self.keys.encrypt(d_pts, self.input_std, enc_seed)
+
+    def decrypt(self, cts: torch.Tensor) -> np.ndarray:
+        ph = self.ctx.to_host_u64(self.keys.phase(cts))
+        w = self.circ.output_width
+        shift = np.uint64(63 - w)
+        u = ((ph + (np.uint64(1) << (shift - np.uint64(1)))) >> shift) & np.uint64((1 << (w + 1)) - 1)
+        u = u.astype(np.int64)
+        if self.circ.output_is_acc:
+            return u - self.circ.output_offset
+        return np.where(u >= (1 << w), u - (1 << (w + 1)), u)      # signed two's complement in w+1 bits
+
+    # ---- server side ---------------------------------------------------------------------------------------------
+    def _channel_range(self, C: int) -> Tuple[int, int, int]:
+        per = (C + self.world - 1) // self.world
+        lo = min(C, self.rank * per)
+        hi = min(C, lo + per)
+        return lo, hi, per
+
+    def _gather(self, local: torch.Tensor, C: int, per: int, hw: int) -> torch.Tensor:
+        """local [(hi-lo)*hw][words] -> full [C*hw][words] on every rank"""
+        if self.world == 1:
+            return local
+        import torch.distributed as dist
+        pad_rows = per * hw
+        if local.shape[0] != pad_rows:
+            buf = torch.zeros(pad_rows, self.words, dtype=local.dtype, device=local.device)
+            buf[: local.shape[0]] = local
+            local = buf
+        full = torch.empty(self.world * pad_rows, self.words, dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(full, local.contiguous(), group=self.pg)
+        return full[: C * hw]
+
+    def run(self, in_cts: torch.Tensor, stats: Optional[RunStats] = None, time_layers: bool = False) -> torch.Tensor:
+        """in_cts [Cin*H*W][words] -> output ciphertexts [n_out][words].  Enqueues on the context stream."""
+        circ, ctx, keys = self.circ, self.ctx, self.keys
+        assert keys is not None, "keygen() first"
+        words = self.words
+        vals: Dict[int, torch.Tensor] = {circ.input_id: in_cts.view(*circ.input_shape, words)}
+        acc_local: Dict[int, Tuple[torch.Tensor, int, int, int]] = {}     # acc id -> (local acc, lo, hi, per)
+        launches0 = launch_count()
+        layer_t = []
+        ev0 = None
+        for op in circ.ops:
+            if time_layers:
+                ev0 = torch.cuda.Event(enable_timing=True); ev0.record()
+            if op.kind == "conv":
+                C = op.out_shape[0]
+                is_out = (op.dst == circ.output_id)
+                lo, hi, per = (0, C, C) if is_out else self._channel_range(C)
+                if hi > lo:
+                    acc = ctx.conv2d(vals[op.src], self._weights[op.dst], op.stride, op.pad, self._bias[op.dst],
+                                     oc_range=(lo, hi), depthwise=op.depthwise)
+                else:
+                    acc = ctx.empty_u64(0, op.out_shape[1], op.out_shape[2], words)
+                acc_local[op.dst] = (acc.view(-1, words), lo, hi, per)
+                if is_out:
+                    vals[op.dst] = acc
+            elif op.kind == "add":
+                C, H, W = op.shape
+                lo, hi, per = self._channel_range(C)
+                half = (1 << (self._lsbs_after(op) - 1)) if self._lsbs_after(op) > 0 else 0
+                const = ((op.offset + half) << (63 - op.acc_bits)) & MASK64
+                if hi > lo:
+                    a = vals[op.a][lo:hi].contiguous()
+                    b = vals[op.b][lo:hi].contiguous()
+                    acc = ctx.axpby(a, op.sa, b, op.sb, body_const=const)
+                else:
+                    acc = ctx.empty_u64(0, H, W, words)
+                acc_local[op.dst] = (acc.view(-1, words), lo, hi, per)
+            else:
+                acc, lo, hi, per = acc_local.pop(op.src)
+                C, H, W = op.shape
+                nloc = acc.shape[0]
+                if nloc > 0:
+                    w = op.acc_bits
+                    for b in range(op.lsbs):
+                        small = keys.keyswitch(BIT_SET, acc, shift=w - b, body_offset=1 << 62)
+                        lut, c = self._bit_luts[(w, b)]
+                        keys.pbs(BIT_SET, small, lut, self._zero_idx[:nloc], mode=1, body_const=c, out=acc)
+                    small = keys.keyswitch(TLU_SET, acc)
+                    out = keys.pbs(TLU_SET, small, self._luts[op.dst], self._lut_index[op.dst][lo * H * W: hi * H * W])
+                    if stats is not None:
+                        stats.pbs_bit += nloc * op.lsbs; stats.pbs_tlu += nloc; stats.keyswitches += nloc * (op.lsbs + 1)
+                else:
+                    out = ctx.empty_u64(0, words)
+                del acc
+                vals[op.dst] = self._gather(out, C, per, H * W).view(C, H, W, words)
+            if time_layers:
+                ev1 = torch.cuda.Event(enable_timing=True); ev1.record()
+                layer_t.append((op.name, ev0, ev1))
+        out = vals[circ.output_id].reshape(-1, words)
+        if stats is not None:
+            stats.launches += launch_count() - launches0
+            if time_layers:
+                torch.cuda.synchronize()
+                stats.layer_seconds = [(n, a.elapsed_time(b) / 1e3) for n, a, b in layer_t]
+        return out

@@ -1,0 +1,74 @@
+"""End-to-end GPU parity: a compiled circuit run by the CUDA executor against the CPU oracle (every output ciphertext
+word) and against the clear integer evaluator (decrypted values, tight-noise toy parameters)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from tfx_b200 import circuit as C
+from tfx_b200.binding import PbsParams
+from tfx_b200.executor import CircuitExecutor, RunStats
+from tfx_b200.resnet_dct import ResidualBlock
+
+pytestmark = pytest.mark.gpu
+
+# insecure toy sets with negligible noise: outputs must equal the clear evaluation exactly
+TOY_TLU = PbsParams(n=96, k=1, N=2048, bsk_base_log=12, bsk_level=3, ksk_base_log=4, ksk_level=6, lwe_std=2.0**-40, glwe_std=2.0**-55)
+TOY_BIT = PbsParams(n=80, k=2, N=1024, bsk_base_log=12, bsk_level=3, ksk_base_log=4, ksk_level=6, lwe_std=2.0**-40, glwe_std=2.0**-55)
+
+
+class TinyNet(nn.Module):
+    def __init__(self, cin=3, c1=4, c2=6, avg=2):
+        super().__init__()
+        self.trunk = nn.Sequential(nn.Conv2d(cin, c1, 1, bias=False), nn.BatchNorm2d(c1), nn.ReLU(),
+                                   ResidualBlock(c1, c1, False), ResidualBlock(c1, c2, True),
+                                   nn.AvgPool2d(avg), nn.Flatten())
+        self.final_feat_dim = c2
+
+    def forward(self, x):
+        return self.trunk(x)
+
+
+def build(seed=0):
+    torch.manual_seed(seed)
+    model = TinyNet().eval()
+    calib = torch.randn(40, 3, 4, 4)
+    circ = C.build_circuit(model, calib, n_bits=5, rounding_threshold_bits=6, p_error=0.01)
+    return model, calib, circ
+
+
+def test_tiny_circuit_matches_oracle_and_clear(gpu_ctx, oracle):
+    from oracle import circuit_oracle as CO
+    model, calib, circ = build()
+    assert any(op.lsbs > 0 for op in circ.lookups()) and any(op.kind == "add" for op in circ.ops)
+    ex = CircuitExecutor(circ, (TOY_TLU, TOY_BIT), ctx=gpu_ctx, input_std=2.0**-50)
+    ex.keygen(seed=5)
+    q_in = C.quantize_input(circ, calib[:1].numpy())[0]
+    cts = ex.encrypt(q_in, enc_seed=6)
+    stats = RunStats()
+    out = ex.run(cts, stats)
+    got = gpu_ctx.to_host_u64(out)
+    # CPU oracle with its own keygen from the same seed
+    keys = CO.OracleKeys((TOY_TLU, TOY_BIT), 5)
+    o_cts = CO.encrypt_input(circ, keys, q_in, 2.0**-50, 6)
+    assert np.array_equal(gpu_ctx.to_host_u64(cts), o_cts)
+    ref = CO.run_circuit(circ, keys, o_cts)
+    assert np.array_equal(got, ref), "GPU circuit output ciphertexts differ from the oracle's"
+    clear = C.evaluate_clear(circ, q_in[None])[0]
+    assert np.array_equal(ex.decrypt(out).reshape(clear.shape), clear)
+    assert np.array_equal(CO.decrypt_output(circ, keys, ref).reshape(clear.shape), clear)
+    cnt = circ.pbs_count()
+    assert stats.pbs_tlu == cnt["tlu"] and stats.pbs_bit == cnt["bit"] and stats.launches > 0
+
+
+def test_quantized_module_execute_matches_simulate(gpu_ctx):
+    from tfx_b200.quantized_module import QuantizedModule
+    torch.manual_seed(1)
+    model = TinyNet().eval()
+    calib = torch.randn(40, 3, 4, 4)
+    qm = QuantizedModule.compile(model, calib, 5, 6, 0.01, params=(TOY_TLU, TOY_BIT))
+    qm.fhe_circuit.keygen(seed=9)
+    x = calib[:2].numpy()
+    y_exec = qm.forward(x, fhe="execute")
+    y_sim = qm.forward(x, fhe="simulate")
+    assert y_exec.shape == (2, 6) and np.array_equal(y_exec, y_sim)
