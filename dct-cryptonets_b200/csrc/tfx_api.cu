@@ -445,6 +445,12 @@ int tfx_linear_axpby(tfx_ctx* ctx, const uint64_t* a_d, int64_t sa, const uint64
     return launch_axpby(a_d, sa, b_d, sb, body_const, count, words, out_d, ctx->sm_count, ctx->stream);
 }
 
+int tfx_probe_rate(tfx_ctx* ctx, int which, double* rate_out) {
+    if (!ctx || !rate_out || which < 0 || which > 1) return set_error(TFX_ERR_ARG, "probe_rate: bad argument");
+    int rc = use_device(ctx); if (rc) return rc;
+    return probe_rate(which, ctx->sm_count, ctx->stream, rate_out);
+}
+
 int tfx_fft_tables(uint32_t N, double* twist_h, double* tw_h) {
     if (!twist_h || !tw_h || N < 16 || (N & (N - 1))) return set_error(TFX_ERR_ARG, "fft_tables: bad argument");
     std::vector<double> twist, tw;

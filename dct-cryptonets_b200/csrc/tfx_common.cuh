@@ -285,6 +285,26 @@ __device__ __forceinline__ void fft_inverse_regs(double2 (&x)[8], int t, double2
     pass_butterflies<LOGM, PassInfo<LOGM, 0>::LO, PassInfo<LOGM, 0>::WD, true>(x, t, tw);
 }
 
+// Inverse transform after the caller has run the LAST pass's butterflies from registers and stored them:
+// loads the next pass and finishes; on return x holds pass-0 elements before untwist / scaling.
+template <int LOGM, typename SYNC>
+__device__ __forceinline__ void fft_inverse_tail(double2 (&x)[8], int t, double2* __restrict__ buf,
+                                                 const double2* __restrict__ tw, SYNC sync) {
+    using PL = FftPlan<LOGM>;
+    if constexpr (PL::P >= 4) {
+        pass_load<LOGM, 2>(x, t, buf);
+        pass_butterflies<LOGM, PassInfo<LOGM, 2>::LO, PassInfo<LOGM, 2>::WD, true>(x, t, tw);
+        pass_store<LOGM, 2>(x, t, buf);
+        sync();
+    }
+    pass_load<LOGM, 1>(x, t, buf);
+    pass_butterflies<LOGM, PassInfo<LOGM, 1>::LO, PassInfo<LOGM, 1>::WD, true>(x, t, tw);
+    pass_store<LOGM, 1>(x, t, buf);
+    sync();
+    pass_load<LOGM, 0>(x, t, buf);
+    pass_butterflies<LOGM, PassInfo<LOGM, 0>::LO, PassInfo<LOGM, 0>::WD, true>(x, t, tw);
+}
+
 // canonical FFT position of element e of thread t after the last forward pass
 template <int LOGM>
 __device__ __forceinline__ int last_pass_index(int t, int e) {

@@ -46,4 +46,6 @@ int launch_conv2d(const uint64_t* in, uint32_t Cin, uint32_t H, uint32_t W, uint
 int launch_axpby(const uint64_t* a, int64_t sa, const uint64_t* b, int64_t sb, uint64_t body_const, size_t count,
                  uint32_t words, uint64_t* out, int sm_count, cudaStream_t s);
 
+int probe_rate(int which, int sm_count, cudaStream_t stream, double* rate);
+
 }  // namespace tfx

@@ -1,13 +1,13 @@
 // tfx_pbs.cu — K1: batched programmable bootstrap (mod-switch, blind rotation, sample extract fused),
 // plus the BSK -> Fourier conversion and the FFT test hooks that share its transform.
 //
-// One CTA owns one ciphertext at a time (grid-stride over the batch).  The GLWE accumulator ((k+1) x N
-// torus words) lives in shared memory for the whole blind rotation.  The CTA is split into (k+1) groups of
-// M/8 threads; group r runs the forward FFTs of the digit polynomials of accumulator component r (levels in
-// sequence), multiplies them with the Fourier bootstrapping key rows (r, lvl, *) streamed from HBM/L2
-// in a thread-major layout (coalesced 16 B per lane), and keeps the (k+1) partial output spectra in
-// registers.  Partial spectra are exchanged through shared memory, then group c runs the inverse FFT of
-// output component c and adds the rounded result into the accumulator.
+// One CTA (M/8 threads, 8 complex points per thread) owns one ciphertext at a time (grid-stride over the
+// batch); two CTAs share an SM for N <= 2048.  The GLWE accumulator ((k+1) x N torus words) lives in shared memory
+// for the whole blind rotation.  Per CMux step the CTA runs, for every accumulator component r and gadget level,
+// the forward FFT of the digit polynomial (rotation, decomposition and twist fused into the first register pass),
+// multiplies the spectrum with the Fourier bootstrapping-key rows (r, lvl, *) streamed from HBM/L2 in a
+// thread-major layout (coalesced 16 B per lane) and accumulates the (k+1) output spectra in registers; then the
+// (k+1) inverse FFTs run from those registers and add the rounded result into the accumulator.
 // Replaces (upstream) concrete-cpu's bootstrap behind reference homomorphic_eval.py:70.
 #include "tfx_common.cuh"
 #include "tfx_internal.h"
@@ -18,13 +18,14 @@ template <int LOGN, int K> struct PbsCfg {
     static constexpr int N = 1 << LOGN;
     static constexpr int LOGM = LOGN - 1;
     static constexpr int M = N / 2;
-    static constexpr int TPF = M / 8;
+    static constexpr int TPF = M / 8;                    // threads per ciphertext (8 complex points each)
     static constexpr int G = K + 1;
-    static constexpr int THREADS = G * TPF;
-    static constexpr int XB = (K > 1 ? K : 1) * M;     // exchange buffer (complex) per group
+    static constexpr int THREADS = TPF;
+    // accumulator + one FFT buffer + twiddle and twist tables + mod-switched mask
     static constexpr size_t smem_bytes(int n) {
-        return (size_t)G * N * 8 + (size_t)G * XB * 16 + (size_t)M * 16 * 2 + (size_t)((n + 1 + 7) / 8 * 8) * 4;
+        return (size_t)G * N * 8 + (size_t)M * 16 + (size_t)M * 16 * 2 + (size_t)((n + 1 + 7) / 8 * 8) * 4;
     }
+    static constexpr int MIN_BLOCKS = (LOGN <= 11) ? 2 : 1;
 };
 
 struct PbsArgs {
@@ -41,43 +42,59 @@ struct PbsArgs {
     uint32_t count;
 };
 
+// signed digit `lvl` (1-based) of x in O(1): raw digit plus the carry of the balanced representation of the
+// lower levels (carry iff lower part >= thr[lvl]); identical to the sequential rule of decompose_digit().
+struct DigitCtx { uint64_t round_add; int top_shift; int base_log; uint64_t mask, half; };
+
+__device__ __forceinline__ double digit_as_double(uint64_t x, const DigitCtx& dc, int shift_in_top, uint64_t low_mask, uint64_t thr) {
+    const uint64_t v = (x + dc.round_add) >> dc.top_shift;            // top base_log*level bits, rounded
+    uint64_t d = (v >> shift_in_top) & dc.mask;
+    d += ((v & low_mask) >= thr) ? 1 : 0;
+    int64_t sd = (int64_t)d;
+    if (d >= dc.half) sd -= (int64_t)(dc.mask + 1);
+    // exact int -> double without the conversion pipe: 1.5 * 2^52 + sd as a bit pattern, minus 1.5 * 2^52
+    return __longlong_as_double(0x4338000000000000LL + sd) - 6755399441055744.0;
+}
+
 template <int LOGN, int K>
-__global__ void __launch_bounds__(PbsCfg<LOGN, K>::THREADS, 1)
+__global__ void __launch_bounds__(PbsCfg<LOGN, K>::THREADS, PbsCfg<LOGN, K>::MIN_BLOCKS)
 pbs_kernel(PbsArgs a) {
     using C = PbsCfg<LOGN, K>;
     constexpr int N = C::N, M = C::M, LOGM = C::LOGM, TPF = C::TPF, G = C::G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* acc = reinterpret_cast<uint64_t*>(smem_raw);                    // [G][N]
-    double2* xbuf = reinterpret_cast<double2*>(acc + (size_t)G * N);          // [G][XB]
-    double2* s_tw = xbuf + (size_t)G * C::XB;                                 // [M]
+    double2* buf = reinterpret_cast<double2*>(acc + (size_t)G * N);           // [M] swizzled
+    double2* s_tw = buf + M;                                                  // [M]
     double2* s_twist = s_tw + M;                                              // [M]
     uint32_t* s_ahat = reinterpret_cast<uint32_t*>(s_twist + M);              // [n+1]
 
-    const int tid = threadIdx.x;
-    const int g = tid / TPF;          // group == accumulator component handled in the forward phase
-    const int t = tid - g * TPF;
-    double2* mybuf = xbuf + (size_t)g * C::XB;
-    uint64_t* myacc = acc + (size_t)g * N;
+    const int t = threadIdx.x;
     auto sync = [] { __syncthreads(); };
 
-    for (int i = tid; i < M; i += C::THREADS) { s_tw[i] = a.tw[i]; s_twist[i] = a.twist[i]; }
+    for (int i = t; i < M; i += TPF) { s_tw[i] = a.tw[i]; s_twist[i] = a.twist[i]; }
+
+    DigitCtx dc;
+    {
+        const int total = a.base_log * a.level;
+        dc.round_add = (total < 64) ? (1ULL << (63 - total)) : 0;
+        dc.top_shift = 64 - total;
+        dc.base_log = a.base_log;
+        dc.mask = (1ULL << a.base_log) - 1;
+        dc.half = 1ULL << (a.base_log - 1);
+    }
 
     for (uint32_t ct = blockIdx.x; ct < a.count; ct += gridDim.x) {
         const uint64_t* in = a.in + (size_t)ct * (a.n + 1);
         __syncthreads();
-        for (uint32_t i = tid; i <= a.n; i += C::THREADS) s_ahat[i] = mod_switch(in[i], LOGN + 1);
+        for (uint32_t i = t; i <= a.n; i += TPF) s_ahat[i] = mod_switch(in[i], LOGN + 1);
         __syncthreads();
         {   // acc = X^{-bhat} * (0, .., 0, LUT)
             const uint64_t* lut = a.luts + (size_t)a.lut_index[ct] * N;
             const uint32_t bhat = s_ahat[a.n];
-            for (int j = tid; j < G * N; j += C::THREADS) {
-                int comp = j / N, jj = j - comp * N;
-                uint64_t v = 0;
-                if (comp == K) {
-                    uint32_t idx = (jj + bhat) & (2 * N - 1);
-                    v = idx < N ? lut[idx] : (uint64_t)0 - lut[idx - N];
-                }
-                acc[j] = v;
+            for (int j = t; j < K * N; j += TPF) acc[j] = 0;
+            for (int j = t; j < N; j += TPF) {
+                uint32_t idx = (j + bhat) & (2 * N - 1);
+                acc[(size_t)K * N + j] = idx < N ? lut[idx] : (uint64_t)0 - lut[idx - N];
             }
         }
         __syncthreads();
@@ -92,86 +109,92 @@ pbs_kernel(PbsArgs a) {
 #pragma unroll
                 for (int e = 0; e < 8; e++) part[c][e] = make_double2(0.0, 0.0);
 
-            for (int lvl = 0; lvl < a.level; lvl++) {
+#pragma unroll 1
+            for (int r = 0; r < G; r++) {
+                const uint64_t* ar = acc + (size_t)r * N;
+#pragma unroll 1
+                for (int lvl = 0; lvl < a.level; lvl++) {
+                    // digit selector for level lvl+1 (1 = most significant)
+                    const int shift_in_top = a.base_log * (a.level - 1 - lvl);
+                    const uint64_t low_mask = (shift_in_top > 0) ? ((1ULL << shift_in_top) - 1) : 0;
+                    // carry threshold of the balanced representation of the `m = level-1-lvl` lower digits:
+                    // (B/2 - 1) * (B^m - 1) / (B - 1) + 1   (== B/2 for m = 1); no lower digits -> never
+                    uint64_t thr = ~0ULL;
+                    if (shift_in_top > 0) {
+                        uint64_t rep = 0;
+                        for (int q = 0; q < a.level - 1 - lvl; q++) rep = (rep << a.base_log) | 1ULL;   // (B^m-1)/(B-1)
+                        thr = (dc.half - 1) * rep + 1;
+                    }
+                    double2 x[8];
+                    // pass-0 input: digit polynomial of X^ahat*acc_r - acc_r, twisted
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        const int jc = t + e * TPF;
+                        const uint32_t s0 = (uint32_t)(jc - (int)ahat) & (2 * N - 1);
+                        const uint64_t r0 = s0 < N ? ar[s0] : (uint64_t)0 - ar[s0 - N];
+                        const uint64_t d0 = r0 - ar[jc];
+                        const uint32_t s1 = (s0 + M) & (2 * N - 1);
+                        const uint64_t r1 = s1 < N ? ar[s1] : (uint64_t)0 - ar[s1 - N];
+                        const uint64_t d1 = r1 - ar[jc + M];
+                        const double2 v = make_double2(digit_as_double(d0, dc, shift_in_top, low_mask, thr),
+                                                       digit_as_double(d1, dc, shift_in_top, low_mask, thr));
+                        x[e] = cmul(v, s_twist[jc]);
+                    }
+                    __syncthreads();                                   // previous transform's last loads are done
+                    fft_forward_regs<LOGM>(x, t, buf, s_tw, sync);
+                    // Fourier MAC with BSK_i rows (r, lvl, c): single fma chain over (r, lvl) ascending
+                    const double2* krow = key_i + ((size_t)(r * a.level + lvl) * G) * M + t;
+#pragma unroll
+                    for (int c = 0; c < G; c++) {
+                        double2 kv[8];
+#pragma unroll
+                        for (int e = 0; e < 8; e++) kv[e] = __ldg(krow + (size_t)c * M + e * TPF);
+#pragma unroll
+                        for (int e = 0; e < 8; e++) {
+                            double re = part[c][e].x, im = part[c][e].y;
+                            re = fma(x[e].x, kv[e].x, re); re = fma(-x[e].y, kv[e].y, re);
+                            im = fma(x[e].x, kv[e].y, im); im = fma(x[e].y, kv[e].x, im);
+                            part[c][e] = make_double2(re, im);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < G; c++) {
                 double2 x[8];
-                // pass-0 input: digit polynomial of X^ahat*acc_g - acc_g, twisted
+#pragma unroll
+                for (int e = 0; e < 8; e++) x[e] = part[c][e];
+                // first inverse pass runs from registers; its store must wait for the previous transform's loads
+                {
+                    using PL = FftPlan<LOGM>;
+                    constexpr int LAST = PL::P - 1;
+                    pass_butterflies<LOGM, PassInfo<LOGM, LAST>::LO, PassInfo<LOGM, LAST>::WD, true>(x, t, s_tw);
+                    __syncthreads();
+                    pass_store<LOGM, LAST>(x, t, buf);
+                    __syncthreads();
+                    fft_inverse_tail<LOGM>(x, t, buf, s_tw, sync);
+                }
+                uint64_t* ac = acc + (size_t)c * N;
 #pragma unroll
                 for (int e = 0; e < 8; e++) {
                     const int jc = t + e * TPF;
-                    uint64_t d0, d1;
-                    {
-                        uint32_t s0 = (uint32_t)(jc - (int)ahat) & (2 * N - 1);
-                        uint64_t r0 = s0 < N ? myacc[s0] : (uint64_t)0 - myacc[s0 - N];
-                        d0 = r0 - myacc[jc];
-                        uint32_t s1 = (uint32_t)(jc + M - (int)ahat) & (2 * N - 1);
-                        uint64_t r1 = s1 < N ? myacc[s1] : (uint64_t)0 - myacc[s1 - N];
-                        d1 = r1 - myacc[jc + M];
-                    }
-                    double2 v = make_double2((double)decompose_digit(d0, a.base_log, a.level, lvl + 1),
-                                             (double)decompose_digit(d1, a.base_log, a.level, lvl + 1));
-                    x[e] = cmul(v, s_twist[jc]);
-                }
-                if (lvl > 0) __syncthreads();                          // previous level's last-pass reads are done
-                fft_forward_regs<LOGM>(x, t, mybuf, s_tw, sync);
-                // Fourier MAC with BSK_i rows (g, lvl, c)
-                const double2* krow = key_i + ((size_t)(g * a.level + lvl) * G) * M;
-#pragma unroll
-                for (int c = 0; c < G; c++) {
-#pragma unroll
-                    for (int e = 0; e < 8; e++) {
-                        const double2 kv = __ldg(krow + (size_t)c * M + e * TPF + t);
-                        double re = part[c][e].x, im = part[c][e].y;
-                        re = fma(x[e].x, kv.x, re); re = fma(-x[e].y, kv.y, re);
-                        im = fma(x[e].x, kv.y, im); im = fma(x[e].y, kv.x, im);
-                        part[c][e] = make_double2(re, im);
-                    }
+                    double2 rr = cmulc(x[e], s_twist[jc]);
+                    ac[jc] += double_to_torus(rr.x * (1.0 / M));
+                    ac[jc + M] += double_to_torus(rr.y * (1.0 / M));
                 }
             }
-            // exchange partial spectra: group g keeps component g, ships the others
-            __syncthreads();                                           // all forward reads of xbuf finished
-#pragma unroll
-            for (int c = 0; c < G; c++) {
-                if (c == g) continue;
-                const int slot = (g < c) ? g : g - 1;                  // position of sender g in receiver c's buffer
-                double2* dst = xbuf + (size_t)c * C::XB + (size_t)slot * M;
-#pragma unroll
-                for (int e = 0; e < 8; e++) dst[e * TPF + t] = part[c][e];
-            }
-            __syncthreads();
-            double2 x[8];
-            {   // F_g = sum over r ascending of partial_r (own partial from registers, the others from smem)
-#pragma unroll
-                for (int r = 0; r < G; r++) {
-                    const bool own = (r == g);
-#pragma unroll
-                    for (int e = 0; e < 8; e++) {
-                        double2 v = part[r][e];
-                        if (!own) v = mybuf[(size_t)((r < g) ? r : r - 1) * M + e * TPF + t];
-                        x[e] = (r == 0) ? v : cadd(x[e], v);
-                    }
-                }
-            }
-            __syncthreads();                                           // exchange reads done before buffers are reused
-            fft_inverse_regs<LOGM>(x, t, mybuf, s_tw, sync);
-#pragma unroll
-            for (int e = 0; e < 8; e++) {
-                const int jc = t + e * TPF;
-                double2 r = cmulc(x[e], s_twist[jc]);
-                myacc[jc] += double_to_torus(r.x * (1.0 / M));
-                myacc[jc + M] += double_to_torus(r.y * (1.0 / M));
-            }
-            __syncthreads();
+            __syncthreads();                                           // accumulator complete before the next rotation reads
         }
 
         // sample extract coefficient 0 -> LWE under the big key
         uint64_t* o = a.out + (size_t)ct * ((size_t)K * N + 1);
-        for (int j = tid; j < K * N; j += C::THREADS) {
+        for (int j = t; j < K * N; j += TPF) {
             int comp = j / N, tt = j - comp * N;
             const uint64_t* ar = acc + (size_t)comp * N;
             uint64_t v = (tt == 0) ? ar[0] : (uint64_t)0 - ar[N - tt];
             if (a.mode == 0) o[j] = v; else o[j] -= v;
         }
-        if (tid == 0) {
+        if (t == 0) {
             uint64_t bv = acc[(size_t)K * N];
             if (a.mode == 0) o[(size_t)K * N] = bv; else o[(size_t)K * N] -= bv + a.body_const;
         }

@@ -82,6 +82,7 @@ SYMBOLS = {
     "tfx_fft_tables": (_I32, [_U32, _VP, _VP]),
     "tfx_fft_forward": (_I32, [_VP, _U32, _VP, _SZ, _VP]),
     "tfx_fft_inverse": (_I32, [_VP, _U32, _VP, _SZ, _VP]),
+    "tfx_probe_rate": (_I32, [_VP, _I32, C.POINTER(C.c_double)]),
     "tfx_launch_count": (_U64, []),
 }
 
@@ -171,6 +172,12 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    def probe_rate(self, which: int) -> float:
+        """0: FP64 FMA FLOP/s, 1: u64 += u32*u64 MAC/s (measured on this device)"""
+        r = C.c_double()
+        _check(self.lib.tfx_probe_rate(self.h, which, C.byref(r)), "tfx_probe_rate")
+        return r.value
 
     # ---- tensor helpers -------------------------------------------------------------------------
     def empty_u64(self, *shape) -> torch.Tensor:

@@ -117,6 +117,8 @@ TFX_API int tfx_fft_tables(uint32_t N, double* twist_h, double* tw_h);
 /* negacyclic FFT of P real polynomials: polys [P][N] (double) -> freq [P][N/2][2] canonical order, and back */
 TFX_API int tfx_fft_forward(tfx_ctx* ctx, uint32_t N, const double* polys_d, size_t P, double* freq_d);
 TFX_API int tfx_fft_inverse(tfx_ctx* ctx, uint32_t N, const double* freq_d, size_t P, uint64_t* torus_d);
+/* machine probes for the roofline denominators: which 0 -> FP64 FMA rate in FLOP/s, 1 -> u64 += u32*u64 rate in MAC/s */
+TFX_API int tfx_probe_rate(tfx_ctx* ctx, int which, double* rate_out);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 TFX_API uint64_t tfx_launch_count(void);
 

@@ -456,8 +456,7 @@ ORC_API void orc_bsk_to_fourier(const uint64_t* bsk, uint32_t n, uint32_t k, uin
  *    in  : u64 [B][n+1] under the small key; luts u64 [T][N]; lut_index u32 [B]
  *    out : u64 [B][kN+1] under the big key.
  *    mode 0: out = result ; mode 1: out -= (result + (0,..,0,body_const))   (rounding chain, A.7 step 4)
- *    MAC order (fixed): partial_r = fma-chain over lvl ascending starting from 0;
- *                       F_c = ((partial_0 + partial_1) + ...) ascending r.
+ *    MAC order (fixed): F_c = one fma chain starting from 0 over (r ascending, lvl ascending).
  * ---------------------------------------------------------------------------------------------- */
 static inline uint32_t mod_switch(uint64_t x, uint32_t log2_2N) {
     return (uint32_t)((((x >> (64 - log2_2N - 1)) + 1) >> 1) & ((1u << log2_2N) - 1));
@@ -494,16 +493,16 @@ ORC_API void orc_pbs(const double* bsk_f, uint32_t n, uint32_t k, uint32_t N, in
                 uint32_t ahat = mod_switch(ct[i], log2_2N);
                 if (ahat == 0) continue;
                 const double* key_i = bsk_f + (uint64_t)i * (k + 1) * level * (k + 1) * N;
+                for (uint32_t q = 0; q < (k + 1) * M; q++) { F[q].re = 0.0; F[q].im = 0.0; }
                 for (uint32_t r = 0; r <= k; r++) {
                     const uint64_t* ar = acc + (uint64_t)r * N;
                     for (uint32_t j = 0; j < N; j++) diff[j] = rot_coeff(ar, N, j, ahat) - ar[j];
-                    for (uint32_t c = 0; c <= k; c++) for (uint32_t q = 0; q < M; q++) { part[c * M + q].re = 0.0; part[c * M + q].im = 0.0; }
                     for (int lvl = 0; lvl < level; lvl++) {
                         for (uint32_t j = 0; j < N; j++) { decompose(diff[j], base_log, level, dg); dpoly[j] = (double)dg[lvl]; }
                         fft_forward(p, dpoly, D);
                         for (uint32_t c = 0; c <= k; c++) {
                             const cplx* K = (const cplx*)(key_i + (((uint64_t)r * level + lvl) * (k + 1) + c) * N);
-                            cplx* pc = part + (uint64_t)c * M;
+                            cplx* pc = F + (uint64_t)c * M;
                             for (uint32_t q = 0; q < M; q++) {
                                 double re = pc[q].re, im = pc[q].im;
                                 re = fma(D[q].re, K[q].re, re); re = fma(-D[q].im, K[q].im, re);
@@ -512,8 +511,6 @@ ORC_API void orc_pbs(const double* bsk_f, uint32_t n, uint32_t k, uint32_t N, in
                             }
                         }
                     }
-                    if (r == 0) memcpy(F, part, sizeof(cplx) * (k + 1) * M);
-                    else for (uint32_t q = 0; q < (k + 1) * M; q++) { F[q].re += part[q].re; F[q].im += part[q].im; }
                 }
                 for (uint32_t c = 0; c <= k; c++) {
                     fft_inverse(p, F + (uint64_t)c * M, dpoly);
