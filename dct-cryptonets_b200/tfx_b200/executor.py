@@ -46,6 +46,30 @@ def bit_lut(acc_bits: int, b: int, N: int) -> Tuple[np.ndarray, int]:
     return np.full(N, (-c) & MASK64, dtype=np.uint64), c
 
 
+def channel_range(C: int, rank: int, world: int) -> Tuple[int, int, int]:
+    """output-channel block [lo, hi) owned by `rank` and the padded block size (SURVEY §8e partition)"""
+    per = (C + world - 1) // world
+    lo = min(C, rank * per)
+    hi = min(C, lo + per)
+    return lo, hi, per
+
+
+def gather_channels(local: torch.Tensor, C: int, per: int, hw: int, world: int, pg=None) -> torch.Tensor:
+    """local [(hi-lo)*hw][words] -> full [C*hw][words] on every rank (all-gather of equal, zero-padded blocks)"""
+    if world == 1:
+        return local
+    import torch.distributed as dist
+    words = local.shape[-1]
+    pad_rows = per * hw
+    if local.shape[0] != pad_rows:
+        buf = torch.zeros(pad_rows, words, dtype=local.dtype, device=local.device)
+        buf[: local.shape[0]] = local
+        local = buf
+    full = torch.empty(world * pad_rows, words, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(full, local.contiguous(), group=pg)
+    return full[: C * hw]
+
+
 @dataclass
 class RunStats:
     seconds: float = 0.0
@@ -54,6 +78,15 @@ class RunStats:
     keyswitches: int = 0
     launches: int = 0
     layer_seconds: Optional[List[Tuple[str, float]]] = None
+    kernel_events: Optional[list] = None          # (class, event0, event1, units) per launch when profiling
+
+    def kernel_seconds(self) -> Dict[str, Tuple[float, int, int]]:
+        """class -> (seconds, launches, units); CUDA-event time on the launching stream, call after a synchronize"""
+        out: Dict[str, Tuple[float, int, int]] = {}
+        for cls, e0, e1, units in (self.kernel_events or []):
+            s, n, u = out.get(cls, (0.0, 0, 0))
+            out[cls] = (s + e0.elapsed_time(e1) / 1e3, n + 1, u + units)
+        return out
 
 
 class CircuitExecutor:
@@ -137,30 +170,29 @@ class CircuitExecutor:
 
     # ---- server side ---------------------------------------------------------------------------------------------
     def _channel_range(self, C: int) -> Tuple[int, int, int]:
-        per = (C + self.world - 1) // self.world
-        lo = min(C, self.rank * per)
-        hi = min(C, lo + per)
-        return lo, hi, per
+        return channel_range(C, self.rank, self.world)
 
     def _gather(self, local: torch.Tensor, C: int, per: int, hw: int) -> torch.Tensor:
-        """local [(hi-lo)*hw][words] -> full [C*hw][words] on every rank"""
-        if self.world == 1:
-            return local
-        import torch.distributed as dist
-        pad_rows = per * hw
-        if local.shape[0] != pad_rows:
-            buf = torch.zeros(pad_rows, self.words, dtype=local.dtype, device=local.device)
-            buf[: local.shape[0]] = local
-            local = buf
-        full = torch.empty(self.world * pad_rows, self.words, dtype=local.dtype, device=local.device)
-        dist.all_gather_into_tensor(full, local.contiguous(), group=self.pg)
-        return full[: C * hw]
+        return gather_channels(local, C, per, hw, self.world, self.pg)
 
-    def run(self, in_cts: torch.Tensor, stats: Optional[RunStats] = None, time_layers: bool = False) -> torch.Tensor:
+    def run(self, in_cts: torch.Tensor, stats: Optional[RunStats] = None, time_layers: bool = False,
+            profile_kernels: bool = False) -> torch.Tensor:
         """in_cts [Cin*H*W][words] -> output ciphertexts [n_out][words].  Enqueues on the context stream."""
         circ, ctx, keys = self.circ, self.ctx, self.keys
         assert keys is not None, "keygen() first"
         words = self.words
+        prof = profile_kernels and stats is not None
+        if prof and stats.kernel_events is None:
+            stats.kernel_events = []
+
+        def timed(cls, units, fn):
+            if not prof:
+                return fn()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); r = fn(); e1.record()
+            stats.kernel_events.append((cls, e0, e1, units))
+            return r
+
         vals: Dict[int, torch.Tensor] = {circ.input_id: in_cts.view(*circ.input_shape, words)}
         acc_local: Dict[int, Tuple[torch.Tensor, int, int, int]] = {}     # acc id -> (local acc, lo, hi, per)
         launches0 = launch_count()
@@ -174,8 +206,9 @@ class CircuitExecutor:
                 is_out = (op.dst == circ.output_id)
                 lo, hi, per = (0, C, C) if is_out else self._channel_range(C)
                 if hi > lo:
-                    acc = ctx.conv2d(vals[op.src], self._weights[op.dst], op.stride, op.pad, self._bias[op.dst],
-                                     oc_range=(lo, hi), depthwise=op.depthwise)
+                    acc = timed("conv", (hi - lo) * op.out_shape[1] * op.out_shape[2],
+                                lambda: ctx.conv2d(vals[op.src], self._weights[op.dst], op.stride, op.pad, self._bias[op.dst],
+                                                   oc_range=(lo, hi), depthwise=op.depthwise))
                 else:
                     acc = ctx.empty_u64(0, op.out_shape[1], op.out_shape[2], words)
                 acc_local[op.dst] = (acc.view(-1, words), lo, hi, per)
@@ -189,7 +222,7 @@ class CircuitExecutor:
                 if hi > lo:
                     a = vals[op.a][lo:hi].contiguous()
                     b = vals[op.b][lo:hi].contiguous()
-                    acc = ctx.axpby(a, op.sa, b, op.sb, body_const=const)
+                    acc = timed("add", a.shape[0] * H * W, lambda: ctx.axpby(a, op.sa, b, op.sb, body_const=const))
                 else:
                     acc = ctx.empty_u64(0, H, W, words)
                 acc_local[op.dst] = (acc.view(-1, words), lo, hi, per)
@@ -200,11 +233,12 @@ class CircuitExecutor:
                 if nloc > 0:
                     w = op.acc_bits
                     for b in range(op.lsbs):
-                        small = keys.keyswitch(BIT_SET, acc, shift=w - b, body_offset=1 << 62)
+                        small = timed("ks_bit", nloc, lambda: keys.keyswitch(BIT_SET, acc, shift=w - b, body_offset=1 << 62))
                         lut, c = self._bit_luts[(w, b)]
-                        keys.pbs(BIT_SET, small, lut, self._zero_idx[:nloc], mode=1, body_const=c, out=acc)
-                    small = keys.keyswitch(TLU_SET, acc)
-                    out = keys.pbs(TLU_SET, small, self._luts[op.dst], self._lut_index[op.dst][lo * H * W: hi * H * W])
+                        timed("pbs_bit", nloc, lambda: keys.pbs(BIT_SET, small, lut, self._zero_idx[:nloc], mode=1, body_const=c, out=acc))
+                    small = timed("ks_tlu", nloc, lambda: keys.keyswitch(TLU_SET, acc))
+                    out = timed("pbs_tlu", nloc, lambda: keys.pbs(TLU_SET, small, self._luts[op.dst],
+                                                                  self._lut_index[op.dst][lo * H * W: hi * H * W]))
                     if stats is not None:
                         stats.pbs_bit += nloc * op.lsbs; stats.pbs_tlu += nloc; stats.keyswitches += nloc * (op.lsbs + 1)
                 else:

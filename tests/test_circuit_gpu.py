@@ -72,3 +72,25 @@ def test_quantized_module_execute_matches_simulate(gpu_ctx):
     y_exec = qm.forward(x, fhe="execute")
     y_sim = qm.forward(x, fhe="simulate")
     assert y_exec.shape == (2, 6) and np.array_equal(y_exec, y_sim)
+
+
+def test_client_server_deployment_roundtrip(gpu_ctx, tmp_path):
+    """FHEModelDev.save -> FHEModelClient (keygen, encrypt) -> bytes -> FHEModelServer.run -> bytes -> client decrypt"""
+    from concrete.ml.deployment import FHEModelClient, FHEModelDev, FHEModelServer
+    from tfx_b200.quantized_module import QuantizedModule
+    torch.manual_seed(2)
+    model = TinyNet().eval()
+    calib = torch.randn(40, 3, 4, 4)
+    qm = QuantizedModule.compile(model, calib, 5, 6, 0.01, params=(TOY_TLU, TOY_BIT))
+    FHEModelDev(str(tmp_path), qm).save()
+    client = FHEModelClient(str(tmp_path))
+    client.generate_private_and_evaluation_keys()
+    eval_keys = client.get_serialized_evaluation_keys()
+    x = calib[:1].numpy()
+    blob = client.quantize_encrypt_serialize(x)
+    server = FHEModelServer(str(tmp_path))
+    result = server.run(blob, eval_keys)
+    assert isinstance(result, bytes)
+    y = client.deserialize_decrypt_dequantize(result)
+    assert np.array_equal(y, qm.forward(x, fhe="simulate"))
+    assert server._ex.keys is not client._ex.keys

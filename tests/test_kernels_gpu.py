@@ -171,3 +171,44 @@ def test_depthwise_sumpool_and_axpby_parity(gpu_ctx, oracle):
     ref = oracle.axpby(x, 1 << 5)
     out = gpu_ctx.axpby(gpu_ctx.to_device_u64(x), 1 << 5)
     assert np.array_equal(gpu_ctx.to_host_u64(out), ref)
+
+
+def test_golden_kats_on_gpu(gpu_ctx):
+    """the committed regression vectors (tests/golden/oracle_kats.json) reproduced by the CUDA path alone"""
+    import json, os
+    kats = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "oracle_kats.json")))
+    p = PbsParams(**kats["params"])
+    ks = KeySet.generate(gpu_ctx, [p], kats["seed"], keep_standard_bsk=True)
+    assert int(ks.get_secret(-1).sum()) == kats["big_key_weight"] and int(ks.get_secret(0).sum()) == kats["small_key_weight"]
+    assert int(np.bitwise_xor.reduce(ks.get_ksk(0).reshape(-1))) == kats["ksk_xor"]
+    assert int(np.bitwise_xor.reduce(ks.get_bsk_standard(0).reshape(-1))) == kats["bsk_xor"]
+    cts = ks.encrypt(gpu_ctx.to_device_u64(np.array(kats["plaintexts"], dtype=np.uint64)), 2.0**-40, kats["seed"] + 1)
+    assert int(np.bitwise_xor.reduce(gpu_ctx.to_host_u64(cts).reshape(-1))) == kats["cts_xor"]
+    sm = ks.keyswitch(0, cts)
+    assert [int(v) for v in gpu_ctx.to_host_u64(sm)[:, -1]] == kats["ks_bodies"]
+    lut = (np.arange(p.N, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15))[None]
+    out = gpu_ctx.to_host_u64(ks.pbs(0, sm, gpu_ctx.to_device_u64(lut), torch.zeros(6, dtype=torch.int32, device=gpu_ctx.device)))
+    assert [int(v) for v in out[:, -1]] == kats["pbs_bodies"]
+    assert int(np.bitwise_xor.reduce(out.reshape(-1))) == kats["pbs_xor"]
+    ks.close()
+
+
+def test_eval_only_keyset_roundtrip(gpu_ctx, oracle):
+    """server side: keys imported as bytes (no secret) give the same PBS / keyswitch results"""
+    p = TOY[1]
+    ks = KeySet.generate(gpu_ctx, [p], 31)
+    ev = KeySet.empty(gpu_ctx, [p])
+    ev.set_ksk(0, ks.get_ksk(0)); ev.set_bsk_fourier(0, ks.get_bsk_fourier(0))
+    rng = np.random.default_rng(8)
+    cts = gpu_ctx.to_device_u64(rng.integers(0, 2**64, size=(5, p.big_dim + 1), dtype=np.uint64))
+    a = ks.keyswitch(0, cts); b = ev.keyswitch(0, cts)
+    assert torch.equal(a, b)
+    luts = gpu_ctx.to_device_u64(rng.integers(0, 2**64, size=(1, p.N), dtype=np.uint64))
+    idx = torch.zeros(5, dtype=torch.int32, device=gpu_ctx.device)
+    assert torch.equal(ks.pbs(0, a, luts, idx), ev.pbs(0, a, luts, idx))
+    with pytest.raises(Exception):
+        ev.encrypt(cts[:, 0].contiguous(), 2.0**-30, 1)         # no secret key on the server side
+    ks.drop_secret()
+    with pytest.raises(Exception):
+        ks.phase(cts)
+    ks.close(); ev.close()
