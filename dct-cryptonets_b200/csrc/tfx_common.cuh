@@ -176,13 +176,19 @@ template <int LOGM, int PASS> struct PassInfo {
 
 __device__ __forceinline__ int swz(int idx) { return idx ^ ((idx >> 3) & 7); }
 
+// "rest" index of sub-group u (0/1) of thread t in a 2-bit pass: [warp][u][lane].  With this placement every pass
+// after the first one touches only the 256 points owned by the thread's warp (index >> 8 == warp), so those passes
+// need warp-level synchronisation only.
+__device__ __forceinline__ int pass2_rest(int t, int u) { return ((t >> 5) << 6) | (u << 5) | (t & 31); }
+
 // index (complex position in the M-array) of element e of thread t in a pass
 template <int LOGM, int LO, int WD>
 __device__ __forceinline__ int elem_index(int t, int e) {
     constexpr int TPF = 1 << (LOGM - 3);
     int rest, f;
     if (WD == 3) { rest = t; f = e; }
-    else { rest = t + (e >> 2) * TPF; f = e & 3; }
+    else { rest = pass2_rest(t, e >> 2); f = e & 3; }
+    (void)TPF;
     return ((rest >> LO) << (LO + WD)) | (f << LO) | (rest & ((1 << LO) - 1));
 }
 
@@ -190,7 +196,6 @@ __device__ __forceinline__ int elem_index(int t, int e) {
 template <int LOGM, int LO, int WD, bool INV>
 __device__ __forceinline__ void pass_butterflies(double2 (&x)[8], int t, const double2* __restrict__ tw) {
     constexpr int M = 1 << LOGM;
-    constexpr int TPF = 1 << (LOGM - 3);
 #pragma unroll
     for (int q = 0; q < WD; q++) {
         const int fb = INV ? q : (WD - 1 - q);            // field bit handled by this stage
@@ -205,7 +210,7 @@ __device__ __forceinline__ void pass_butterflies(double2 (&x)[8], int t, const d
                 double2 a = x[e], b = x[eb];
                 x[e] = cadd(a, b); x[eb] = csub(a, b);
             } else {
-                const int rest = (WD == 3) ? t : (t + (e >> 2) * TPF);
+                const int rest = (WD == 3) ? t : pass2_rest(t, e >> 2);
                 const int j = ((f & ((1 << fb) - 1)) << LO) | (rest & ((1 << LO) - 1));
                 const double2 w = tw[off + j];
                 if (!INV) {
@@ -223,12 +228,18 @@ __device__ __forceinline__ void pass_butterflies(double2 (&x)[8], int t, const d
 
 template <int LOGM, int PASS>
 __device__ __forceinline__ void pass_store(const double2 (&x)[8], int t, double2* __restrict__ buf) {
+#ifdef TFX_EXP_NOSMEM
+    return;
+#endif
     using PI = PassInfo<LOGM, PASS>;
 #pragma unroll
     for (int e = 0; e < 8; e++) buf[swz(elem_index<LOGM, PI::LO, PI::WD>(t, e))] = x[e];
 }
 template <int LOGM, int PASS>
 __device__ __forceinline__ void pass_load(double2 (&x)[8], int t, const double2* __restrict__ buf) {
+#ifdef TFX_EXP_NOSMEM
+    return;
+#endif
     using PI = PassInfo<LOGM, PASS>;
 #pragma unroll
     for (int e = 0; e < 8; e++) x[e] = buf[swz(elem_index<LOGM, PI::LO, PI::WD>(t, e))];
@@ -237,9 +248,10 @@ __device__ __forceinline__ void pass_load(double2 (&x)[8], int t, const double2*
 // Forward passes 1..P-1 given pass-0 INPUT values already in x (pass-0 element order: index = t + e*TPF).
 // On return x holds the frequency-domain values of the last pass's elements (index elem_index<LAST>(t, e)).
 // SYNC is a functor performing the barrier for the threads sharing `buf`.
-template <int LOGM, typename SYNC>
+// SYNC_CTA orders the first (cross-warp) exchange, SYNC_WARP the later, warp-local ones.
+template <int LOGM, typename SYNC_CTA, typename SYNC_WARP>
 __device__ __forceinline__ void fft_forward_regs(double2 (&x)[8], int t, double2* __restrict__ buf,
-                                                 const double2* __restrict__ tw, SYNC sync) {
+                                                 const double2* __restrict__ tw, SYNC_CTA sync, SYNC_WARP wsync) {
     using PL = FftPlan<LOGM>;
     pass_butterflies<LOGM, PassInfo<LOGM, 0>::LO, PassInfo<LOGM, 0>::WD, false>(x, t, tw);
     pass_store<LOGM, 0>(x, t, buf);
@@ -247,18 +259,154 @@ __device__ __forceinline__ void fft_forward_regs(double2 (&x)[8], int t, double2
     pass_load<LOGM, 1>(x, t, buf);
     pass_butterflies<LOGM, PassInfo<LOGM, 1>::LO, PassInfo<LOGM, 1>::WD, false>(x, t, tw);
     if constexpr (PL::P >= 3) {
-        pass_store<LOGM, 1>(x, t, buf);
-        sync();
+        pass_store<LOGM, 1>(x, t, buf);                 // in place: a thread rewrites exactly the elements it loaded
+        wsync();
         pass_load<LOGM, 2>(x, t, buf);
         pass_butterflies<LOGM, PassInfo<LOGM, 2>::LO, PassInfo<LOGM, 2>::WD, false>(x, t, tw);
     }
     if constexpr (PL::P >= 4) {
         pass_store<LOGM, 2>(x, t, buf);
-        sync();
+        wsync();
         pass_load<LOGM, 3>(x, t, buf);
         pass_butterflies<LOGM, PassInfo<LOGM, 3>::LO, PassInfo<LOGM, 3>::WD, false>(x, t, tw);
     }
 }
+template <int LOGM, typename SYNC>
+__device__ __forceinline__ void fft_forward_regs(double2 (&x)[8], int t, double2* __restrict__ buf,
+                                                 const double2* __restrict__ tw, SYNC sync) {
+    fft_forward_regs<LOGM>(x, t, buf, tw, sync, sync);
+}
+
+// ---- twiddles of a pass preloaded into registers (issued before the preceding barrier so their shared-memory
+//      latency overlaps the barrier wait and the data loads) ----------------------------------------------------
+// slot layout: stage with field bit fb uses slots [(1 << WD) - (2 << fb), ...) indexed by the low fb bits of f
+template <int WD> struct TwSlots { static constexpr int N = (1 << WD) - 1; };
+
+template <int LOGM, int LO, int WD>
+__device__ __forceinline__ void load_tw(double2 (&w)[7], int t, const double2* __restrict__ tw) {
+    constexpr int M = 1 << LOGM;
+    const int rest_lo = ((WD == 3) ? t : pass2_rest(t, 0)) & ((1 << LO) - 1);
+#pragma unroll
+    for (int fb = WD - 1; fb >= 0; fb--) {
+        const int half = 1 << (LO + fb);
+        if (half == 1) continue;
+        const int off = M - 2 * half;
+        const int base = (1 << WD) - (2 << fb);
+#pragma unroll
+        for (int fl = 0; fl < (1 << fb); fl++) {
+            if (LO == 0 && (fl == 0 || 2 * fl == half)) continue;           // exactly 1 and i: handled without a multiply
+            w[base + fl] = tw[off + ((fl << LO) | rest_lo)];
+        }
+    }
+}
+
+template <int LOGM, int LO, int WD, bool INV>
+__device__ __forceinline__ void pass_butterflies_w(double2 (&x)[8], const double2 (&w)[7]) {
+#ifdef TFX_EXP_NOMATH
+    return;
+#endif
+#pragma unroll
+    for (int q = 0; q < WD; q++) {
+        const int fb = INV ? q : (WD - 1 - q);
+        const int half = 1 << (LO + fb);
+        const int base = (1 << WD) - (2 << fb);
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int f = (WD == 3) ? e : (e & 3);
+            if (f & (1 << fb)) continue;
+            const int eb = e | (1 << fb);
+            const int fl = f & ((1 << fb) - 1);
+            const bool is_one = (half == 1) || (LO == 0 && fl == 0);
+            const bool is_i = (half != 1) && (LO == 0) && (2 * fl == half);
+            if (!INV) {
+                const double2 a = x[e], b = x[eb];
+                x[e] = cadd(a, b);
+                const double2 d = csub(a, b);
+                if (is_one) x[eb] = d;
+                else if (is_i) x[eb] = make_double2(-d.y, d.x);              // d * i
+                else x[eb] = cmul(d, w[base + fl]);
+            } else {
+                double2 b = x[eb];
+                if (is_one) {}
+                else if (is_i) b = make_double2(b.y, -b.x);                  // b * conj(i)
+                else b = cmulc(b, w[base + fl]);
+                const double2 a = x[e];
+                x[e] = cadd(a, b); x[eb] = csub(a, b);
+            }
+        }
+    }
+}
+
+// ---- two transforms interleaved in one thread (independent instruction streams hide shared-memory latency) ----
+#define TFX_TW(P) load_tw<LOGM, PassInfo<LOGM, P>::LO, PassInfo<LOGM, P>::WD>(w, t, tw);
+#define TFX_PASS2(P, INV) \
+    pass_butterflies_w<LOGM, PassInfo<LOGM, P>::LO, PassInfo<LOGM, P>::WD, INV>(xa, w); \
+    if (DUAL) pass_butterflies_w<LOGM, PassInfo<LOGM, P>::LO, PassInfo<LOGM, P>::WD, INV>(xb, w);
+#define TFX_STORE2(P) pass_store<LOGM, P>(xa, t, bufa); if (DUAL) pass_store<LOGM, P>(xb, t, bufb);
+#define TFX_LOAD2(P) pass_load<LOGM, P>(xa, t, bufa); if (DUAL) pass_load<LOGM, P>(xb, t, bufb);
+
+// forward: xa/xb hold pass-0 inputs, w the pass-0 twiddles (load_tw<.., pass 0>); on return xa/xb hold the spectra
+template <int LOGM, bool DUAL, typename SYNC_CTA, typename SYNC_WARP>
+__device__ __forceinline__ void fft_forward_regs2(double2 (&xa)[8], double2 (&xb)[8], double2 (&w)[7], int t,
+                                                  double2* __restrict__ bufa, double2* __restrict__ bufb,
+                                                  const double2* __restrict__ tw, SYNC_CTA sync, SYNC_WARP wsync) {
+    using PL = FftPlan<LOGM>;
+    TFX_PASS2(0, false)
+    TFX_TW(1)
+    sync();                                   // every warp is done reading the buffers' previous contents
+    TFX_STORE2(0)
+    sync();
+    TFX_LOAD2(1)
+    TFX_PASS2(1, false)
+    if constexpr (PL::P >= 3) {
+        TFX_STORE2(1)
+        TFX_TW(2)
+        wsync();
+        TFX_LOAD2(2)
+        TFX_PASS2(2, false)
+    }
+    if constexpr (PL::P >= 4) {
+        TFX_STORE2(2)
+        TFX_TW(3)
+        wsync();
+        TFX_LOAD2(3)
+        TFX_PASS2(3, false)
+    }
+}
+
+// inverse: xa/xb hold spectra (last-pass element order); on return pass-0 elements before untwist / scaling
+template <int LOGM, bool DUAL, typename SYNC_CTA, typename SYNC_WARP>
+__device__ __forceinline__ void fft_inverse_regs2(double2 (&xa)[8], double2 (&xb)[8], int t, double2* __restrict__ bufa,
+                                                  double2* __restrict__ bufb, const double2* __restrict__ tw,
+                                                  SYNC_CTA sync, SYNC_WARP wsync) {
+    using PL = FftPlan<LOGM>;
+    constexpr int LAST = PL::P - 1;
+    double2 w[7];
+    TFX_TW(LAST)
+    TFX_PASS2(LAST, true)
+    sync();                                   // every warp is done reading the buffers' previous contents
+    TFX_STORE2(LAST)
+    if constexpr (PL::P >= 4) {
+        TFX_TW(2)
+        wsync();
+        TFX_LOAD2(2)
+        TFX_PASS2(2, true)
+        TFX_STORE2(2)
+    }
+    TFX_TW(1)
+    wsync();
+    TFX_LOAD2(1)
+    TFX_PASS2(1, true)
+    TFX_STORE2(1)
+    TFX_TW(0)
+    sync();
+    TFX_LOAD2(0)
+    TFX_PASS2(0, true)
+}
+#undef TFX_TW
+#undef TFX_PASS2
+#undef TFX_STORE2
+#undef TFX_LOAD2
 
 // Inverse: x holds last-pass elements in the frequency domain; on return x holds pass-0 elements
 // (index t + e*TPF) BEFORE the untwist / 1/M scaling.
@@ -287,15 +435,17 @@ __device__ __forceinline__ void fft_inverse_regs(double2 (&x)[8], int t, double2
 
 // Inverse transform after the caller has run the LAST pass's butterflies from registers and stored them:
 // loads the next pass and finishes; on return x holds pass-0 elements before untwist / scaling.
-template <int LOGM, typename SYNC>
+// Precondition: the last pass's values were stored and a warp-level sync done.  Warp-local passes use wsync,
+// the final cross-warp exchange uses sync.
+template <int LOGM, typename SYNC_CTA, typename SYNC_WARP>
 __device__ __forceinline__ void fft_inverse_tail(double2 (&x)[8], int t, double2* __restrict__ buf,
-                                                 const double2* __restrict__ tw, SYNC sync) {
+                                                 const double2* __restrict__ tw, SYNC_CTA sync, SYNC_WARP wsync) {
     using PL = FftPlan<LOGM>;
     if constexpr (PL::P >= 4) {
         pass_load<LOGM, 2>(x, t, buf);
         pass_butterflies<LOGM, PassInfo<LOGM, 2>::LO, PassInfo<LOGM, 2>::WD, true>(x, t, tw);
         pass_store<LOGM, 2>(x, t, buf);
-        sync();
+        wsync();
     }
     pass_load<LOGM, 1>(x, t, buf);
     pass_butterflies<LOGM, PassInfo<LOGM, 1>::LO, PassInfo<LOGM, 1>::WD, true>(x, t, tw);

@@ -9,6 +9,7 @@
 // thread-major layout (coalesced 16 B per lane) and accumulates the (k+1) output spectra in registers; then the
 // (k+1) inverse FFTs run from those registers and add the rounded result into the accumulator.
 // Replaces (upstream) concrete-cpu's bootstrap behind reference homomorphic_eval.py:70.
+#include <stdlib.h>
 #include "tfx_common.cuh"
 #include "tfx_internal.h"
 
@@ -21,9 +22,9 @@ template <int LOGN, int K> struct PbsCfg {
     static constexpr int TPF = M / 8;                    // threads per ciphertext (8 complex points each)
     static constexpr int G = K + 1;
     static constexpr int THREADS = TPF;
-    // accumulator + one FFT buffer + twiddle and twist tables + mod-switched mask
-    static constexpr size_t smem_bytes(int n) {
-        return (size_t)G * N * 8 + (size_t)M * 16 + (size_t)M * 16 * 2 + (size_t)((n + 1 + 7) / 8 * 8) * 4;
+    // accumulator + two FFT buffers (alternating per transform) + twiddle and twist tables
+    static constexpr size_t smem_bytes(int) {
+        return (size_t)G * N * 8 + (size_t)M * 16 * 2 + (size_t)M * 16 * 2;
     }
     static constexpr int MIN_BLOCKS = (LOGN <= 11) ? 2 : 1;
 };
@@ -63,13 +64,15 @@ pbs_kernel(PbsArgs a) {
     constexpr int N = C::N, M = C::M, LOGM = C::LOGM, TPF = C::TPF, G = C::G;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* acc = reinterpret_cast<uint64_t*>(smem_raw);                    // [G][N]
-    double2* buf = reinterpret_cast<double2*>(acc + (size_t)G * N);           // [M] swizzled
-    double2* s_tw = buf + M;                                                  // [M]
+    double2* bufs = reinterpret_cast<double2*>(acc + (size_t)G * N);          // [2][M] swizzled, alternate per transform
+    double2* s_tw = bufs + 2 * M;                                             // [M]
     double2* s_twist = s_tw + M;                                              // [M]
-    uint32_t* s_ahat = reinterpret_cast<uint32_t*>(s_twist + M);              // [n+1]
 
     const int t = threadIdx.x;
     auto sync = [] { __syncthreads(); };
+    auto wsync = [] { __syncwarp(); };
+    double2* bufa = bufs;
+    double2* bufb = bufs + M;
 
     for (int i = t; i < M; i += TPF) { s_tw[i] = a.tw[i]; s_twist[i] = a.twist[i]; }
 
@@ -82,15 +85,47 @@ pbs_kernel(PbsArgs a) {
         dc.mask = (1ULL << a.base_log) - 1;
         dc.half = 1ULL << (a.base_log - 1);
     }
+    const int n_fwd = G * a.level;                 // forward transforms per CMux step, index f = r * level + lvl
+
+    // pass-0 input of forward transform f: digit polynomial (level f % level) of X^ahat * acc_r - acc_r, twisted
+    auto load_digits = [&](double2 (&x)[8], int f, uint32_t ahat) {
+        const int r = f / a.level, lvl = f - r * a.level;
+        const uint64_t* ar = acc + (size_t)r * N;
+        const int shift_in_top = a.base_log * (a.level - 1 - lvl);
+        const uint64_t low_mask = (shift_in_top > 0) ? ((1ULL << shift_in_top) - 1) : 0;
+        // carry threshold of the balanced representation of the m = level-1-lvl lower digits:
+        // (B/2 - 1) * (B^m - 1) / (B - 1) + 1  (== B/2 for m = 1); no lower digits -> never
+        uint64_t thr = ~0ULL;
+        if (shift_in_top > 0) {
+            uint64_t rep = 0;
+            for (int q = 0; q < a.level - 1 - lvl; q++) rep = (rep << a.base_log) | 1ULL;
+            thr = (dc.half - 1) * rep + 1;
+        }
+#ifdef TFX_EXP_NODIGITS
+        for (int e = 0; e < 8; e++) x[e] = make_double2((double)(t + e + f), (double)ahat);
+        return;
+#endif
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int jc = t + e * TPF;
+            const uint32_t s0 = (uint32_t)(jc - (int)ahat) & (2 * N - 1);
+            const uint64_t r0 = s0 < N ? ar[s0] : (uint64_t)0 - ar[s0 - N];
+            const uint64_t d0 = r0 - ar[jc];
+            const uint32_t s1 = (s0 + M) & (2 * N - 1);
+            const uint64_t r1 = s1 < N ? ar[s1] : (uint64_t)0 - ar[s1 - N];
+            const uint64_t d1 = r1 - ar[jc + M];
+            const double2 v = make_double2(digit_as_double(d0, dc, shift_in_top, low_mask, thr),
+                                           digit_as_double(d1, dc, shift_in_top, low_mask, thr));
+            x[e] = cmul(v, s_twist[jc]);
+        }
+    };
 
     for (uint32_t ct = blockIdx.x; ct < a.count; ct += gridDim.x) {
         const uint64_t* in = a.in + (size_t)ct * (a.n + 1);
         __syncthreads();
-        for (uint32_t i = t; i <= a.n; i += TPF) s_ahat[i] = mod_switch(in[i], LOGN + 1);
-        __syncthreads();
         {   // acc = X^{-bhat} * (0, .., 0, LUT)
             const uint64_t* lut = a.luts + (size_t)a.lut_index[ct] * N;
-            const uint32_t bhat = s_ahat[a.n];
+            const uint32_t bhat = mod_switch(__ldg(in + a.n), LOGN + 1);
             for (int j = t; j < K * N; j += TPF) acc[j] = 0;
             for (int j = t; j < N; j += TPF) {
                 uint32_t idx = (j + bhat) & (2 * N - 1);
@@ -99,89 +134,87 @@ pbs_kernel(PbsArgs a) {
         }
         __syncthreads();
 
+        uint64_t a_next = __ldg(in);                                   // mask word of the next step, fetched one step ahead
         for (uint32_t i = 0; i < a.n; i++) {
-            const uint32_t ahat = s_ahat[i];
+            const uint32_t ahat = mod_switch(a_next, LOGN + 1);
+            a_next = __ldg(in + i + 1);                                // (word n is the body: harmless, unused)
             if (ahat == 0) continue;                                   // CTA-uniform
-            const double2* key_i = a.bsk + (size_t)i * G * a.level * G * M;
+            const double2* key_i = a.bsk + (size_t)i * G * a.level * G * M + t;
             double2 part[G][8];
 #pragma unroll
             for (int c = 0; c < G; c++)
 #pragma unroll
                 for (int e = 0; e < 8; e++) part[c][e] = make_double2(0.0, 0.0);
 
-#pragma unroll 1
-            for (int r = 0; r < G; r++) {
-                const uint64_t* ar = acc + (size_t)r * N;
-#pragma unroll 1
-                for (int lvl = 0; lvl < a.level; lvl++) {
-                    // digit selector for level lvl+1 (1 = most significant)
-                    const int shift_in_top = a.base_log * (a.level - 1 - lvl);
-                    const uint64_t low_mask = (shift_in_top > 0) ? ((1ULL << shift_in_top) - 1) : 0;
-                    // carry threshold of the balanced representation of the `m = level-1-lvl` lower digits:
-                    // (B/2 - 1) * (B^m - 1) / (B - 1) + 1   (== B/2 for m = 1); no lower digits -> never
-                    uint64_t thr = ~0ULL;
-                    if (shift_in_top > 0) {
-                        uint64_t rep = 0;
-                        for (int q = 0; q < a.level - 1 - lvl; q++) rep = (rep << a.base_log) | 1ULL;   // (B^m-1)/(B-1)
-                        thr = (dc.half - 1) * rep + 1;
-                    }
-                    double2 x[8];
-                    // pass-0 input: digit polynomial of X^ahat*acc_r - acc_r, twisted
+            // Fourier MAC of spectrum x with BSK_i rows (f, c): one fma chain over f ascending
+            auto mac = [&](const double2 (&x)[8], int f) {
+#ifdef TFX_EXP_NOMAC
+                for (int e = 0; e < 8; e++) part[f % G][e] = x[e];
+                return;
+#endif
+                const double2* krow = key_i + (size_t)f * G * M;
+#pragma unroll
+                for (int c = 0; c < G; c++) {
 #pragma unroll
                     for (int e = 0; e < 8; e++) {
-                        const int jc = t + e * TPF;
-                        const uint32_t s0 = (uint32_t)(jc - (int)ahat) & (2 * N - 1);
-                        const uint64_t r0 = s0 < N ? ar[s0] : (uint64_t)0 - ar[s0 - N];
-                        const uint64_t d0 = r0 - ar[jc];
-                        const uint32_t s1 = (s0 + M) & (2 * N - 1);
-                        const uint64_t r1 = s1 < N ? ar[s1] : (uint64_t)0 - ar[s1 - N];
-                        const uint64_t d1 = r1 - ar[jc + M];
-                        const double2 v = make_double2(digit_as_double(d0, dc, shift_in_top, low_mask, thr),
-                                                       digit_as_double(d1, dc, shift_in_top, low_mask, thr));
-                        x[e] = cmul(v, s_twist[jc]);
-                    }
-                    __syncthreads();                                   // previous transform's last loads are done
-                    fft_forward_regs<LOGM>(x, t, buf, s_tw, sync);
-                    // Fourier MAC with BSK_i rows (r, lvl, c): single fma chain over (r, lvl) ascending
-                    const double2* krow = key_i + ((size_t)(r * a.level + lvl) * G) * M + t;
-#pragma unroll
-                    for (int c = 0; c < G; c++) {
-                        double2 kv[8];
-#pragma unroll
-                        for (int e = 0; e < 8; e++) kv[e] = __ldg(krow + (size_t)c * M + e * TPF);
-#pragma unroll
-                        for (int e = 0; e < 8; e++) {
-                            double re = part[c][e].x, im = part[c][e].y;
-                            re = fma(x[e].x, kv[e].x, re); re = fma(-x[e].y, kv[e].y, re);
-                            im = fma(x[e].x, kv[e].y, im); im = fma(x[e].y, kv[e].x, im);
-                            part[c][e] = make_double2(re, im);
-                        }
+                        const double2 kv = __ldg(krow + (size_t)c * M + e * TPF);
+                        double re = part[c][e].x, im = part[c][e].y;
+                        re = fma(x[e].x, kv.x, re); re = fma(-x[e].y, kv.y, re);
+                        im = fma(x[e].x, kv.y, im); im = fma(x[e].y, kv.x, im);
+                        part[c][e] = make_double2(re, im);
                     }
                 }
+            };
+
+            // forward transforms two at a time (independent streams interleaved in every thread)
+#pragma unroll 1
+            for (int f = 0; f + 1 < n_fwd; f += 2) {
+                double2 xa[8], xb[8], w[7];
+                load_tw<LOGM, PassInfo<LOGM, 0>::LO, PassInfo<LOGM, 0>::WD>(w, t, s_tw);
+                load_digits(xa, f, ahat);
+                load_digits(xb, f + 1, ahat);
+                fft_forward_regs2<LOGM, true>(xa, xb, w, t, bufa, bufb, s_tw, sync, wsync);
+                mac(xa, f);
+                mac(xb, f + 1);
             }
-#pragma unroll
-            for (int c = 0; c < G; c++) {
-                double2 x[8];
-#pragma unroll
-                for (int e = 0; e < 8; e++) x[e] = part[c][e];
-                // first inverse pass runs from registers; its store must wait for the previous transform's loads
-                {
-                    using PL = FftPlan<LOGM>;
-                    constexpr int LAST = PL::P - 1;
-                    pass_butterflies<LOGM, PassInfo<LOGM, LAST>::LO, PassInfo<LOGM, LAST>::WD, true>(x, t, s_tw);
-                    __syncthreads();
-                    pass_store<LOGM, LAST>(x, t, buf);
-                    __syncthreads();
-                    fft_inverse_tail<LOGM>(x, t, buf, s_tw, sync);
-                }
+            if (n_fwd & 1) {
+                double2 xa[8], w[7];
+                load_tw<LOGM, PassInfo<LOGM, 0>::LO, PassInfo<LOGM, 0>::WD>(w, t, s_tw);
+                load_digits(xa, n_fwd - 1, ahat);
+                fft_forward_regs2<LOGM, false>(xa, xa, w, t, bufa, bufb, s_tw, sync, wsync);
+                mac(xa, n_fwd - 1);
+            }
+
+            auto add_back = [&](const double2 (&x)[8], int c) {
                 uint64_t* ac = acc + (size_t)c * N;
+#ifdef TFX_EXP_NOADDBACK
+                if (x[0].x == 123.456) ac[t] = 1;
+                return;
+#endif
 #pragma unroll
                 for (int e = 0; e < 8; e++) {
                     const int jc = t + e * TPF;
-                    double2 rr = cmulc(x[e], s_twist[jc]);
+                    const double2 rr = cmulc(x[e], s_twist[jc]);
                     ac[jc] += double_to_torus(rr.x * (1.0 / M));
                     ac[jc + M] += double_to_torus(rr.y * (1.0 / M));
                 }
+            };
+            // inverse transforms, two output components at a time
+#pragma unroll
+            for (int c = 0; c + 1 < G; c += 2) {
+                double2 xa[8], xb[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) { xa[e] = part[c][e]; xb[e] = part[c + 1][e]; }
+                fft_inverse_regs2<LOGM, true>(xa, xb, t, bufa, bufb, s_tw, sync, wsync);
+                add_back(xa, c);
+                add_back(xb, c + 1);
+            }
+            if (G & 1) {
+                double2 xa[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) xa[e] = part[G - 1][e];
+                fft_inverse_regs2<LOGM, false>(xa, xa, t, bufa, bufb, s_tw, sync, wsync);
+                add_back(xa, G - 1);
             }
             __syncthreads();                                           // accumulator complete before the next rotation reads
         }
@@ -304,6 +337,8 @@ static int launch_pbs_t(const PbsArgs& a, int sm_count, cudaStream_t stream) {
     if (blocks_per_sm < 1) return set_error(TFX_ERR_UNSUPPORTED, "pbs: kernel does not fit on an SM");
     unsigned grid = (unsigned)sm_count * blocks_per_sm;
     if (grid > a.count) grid = a.count;
+    // measurement knob (profiles/r01_pbs_experiments.md): cap the grid, e.g. to one CTA per SM
+    if (const char* cap = getenv("TFX_PBS_GRID_CAP")) { unsigned g = (unsigned)atoi(cap); if (g && g < grid) grid = g; }
     pbs_kernel<LOGN, K><<<grid, C::THREADS, smem, stream>>>(a);
     count_launch();
     return check_launch("pbs_kernel");

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtfx_b200.so")
+LIB_PATH = os.environ.get("TFX_LIB", os.path.join(_HERE, "libtfx_b200.so"))    # TFX_LIB: experiment builds only
 
 
 class TfxError(RuntimeError):
