@@ -271,7 +271,8 @@ def run_gpu(args):
                 "frac": flops / sec / dfma, "peak_source": "DFMA rate measured live by tfx_probe_rate (MEASURED_PEAKS.json has no FP64 figure)",
                 "flops_per_pbs": P.pbs_flops(dom_p), "pbs_per_launch": units / max(1, nl), "avg_launch_ms": sec / max(1, nl) * 1e3,
                 "share_of_step": sec / total_kernel_s,
-                "traffic": prof.get(dom, {}).get("dram_bytes_per_launch"),
+                "traffic": (prof.get(dom, {}).get("dram_bytes_per_unit") or 0) * units / max(1, nl) or None,
+                "traffic_source": prof.get("source"),
                 "hbm": {"achieved": nl * P.bsk_bytes(dom_p) / sec / 1e9, "peak": hbm_peak, "unit": "GB/s",
                         "frac": nl * P.bsk_bytes(dom_p) / sec / 1e9 / hbm_peak, "peak_source": peak_src,
                         "note": "algorithmic bootstrapping-key bytes per launch (one pass over the key serves the whole batch)"},

@@ -40,11 +40,14 @@ keyswitch_kernel(KsArgs a) {
     const uint32_t half = 1u << (bl - 1), mask = (1u << bl) - 1;
     const int total = bl * l;
 
-    uint64_t acc[4][4];
+    // split accumulators: lo64 += d * K_lo (IMAD.WIDE.U32, carries stay inside the 64-bit word), hi32 += d * K_hi (IMAD);
+    // result mod 2^64 = lo64 + (hi32 << 32).  Two integer multiply-adds per u64 MAC, no 64-bit pair shuffling.
+    uint64_t acc_lo[4][4];
+    uint32_t acc_hi[4][4];
 #pragma unroll
     for (int r = 0; r < 4; r++)
 #pragma unroll
-        for (int c = 0; c < 4; c++) acc[r][c] = 0;
+        for (int c = 0; c < 4; c++) { acc_lo[r][c] = 0; acc_hi[r][c] = 0; }
 
     for (uint32_t w0 = 0; w0 < a.big_dim; w0 += words_per_chunk) {
         __syncthreads();
@@ -77,9 +80,14 @@ keyswitch_kernel(KsArgs a) {
             const uint32_t d[4] = {dg.x, dg.y, dg.z, dg.w};
             const uint64_t kv[4] = {ka.x, ka.y, kb.x, kb.y};
 #pragma unroll
-            for (int r = 0; r < 4; r++)
+            for (int c = 0; c < 4; c++) {
+                const uint32_t klo = (uint32_t)kv[c], khi = (uint32_t)(kv[c] >> 32);
 #pragma unroll
-                for (int c = 0; c < 4; c++) acc[r][c] += (uint64_t)d[r] * kv[c];
+                for (int r = 0; r < 4; r++) {
+                    acc_lo[r][c] += (uint64_t)d[r] * klo;
+                    acc_hi[r][c] += d[r] * khi;
+                }
+            }
         }
     }
     // epilogue: out = init - (acc - corr)
@@ -93,7 +101,8 @@ keyswitch_kernel(KsArgs a) {
             if (j > a.n) continue;
             uint64_t init = 0;
             if (j == a.n) init = (a.in[(size_t)b * (a.big_dim + 1) + a.big_dim] << a.shift) + a.body_offset;
-            a.out[(size_t)b * (a.n + 1) + j] = init - acc[r][c] + a.corr[j];
+            const uint64_t acc = acc_lo[r][c] + ((uint64_t)acc_hi[r][c] << 32);
+            a.out[(size_t)b * (a.n + 1) + j] = init - acc + a.corr[j];
         }
     }
 }
