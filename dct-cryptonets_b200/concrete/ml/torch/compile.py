@@ -11,15 +11,16 @@ import torch
 from tfx_b200.quantized_module import QuantizedModule
 
 
-def _rounding_bits(rounding_threshold_bits) -> int:
+def _rounding(rounding_threshold_bits):
+    """int or {"n_bits": int, "method": "exact" | "approximate"} (reference homomorphic_eval.py:279-280, README.md:96-113)"""
     if rounding_threshold_bits is None:
-        return 16
+        return 16, "exact"
     if isinstance(rounding_threshold_bits, dict):
-        if rounding_threshold_bits.get("method", "exact").lower() != "exact":
-            raise NotImplementedError("approximate rounding (README.md:96-113 of the reference) is not implemented; "
-                                      "the published numbers use exact rounding")
-        return int(rounding_threshold_bits["n_bits"])
-    return int(rounding_threshold_bits)
+        method = str(rounding_threshold_bits.get("method", "exact")).lower()
+        if method not in ("exact", "approximate"):
+            raise ValueError(f"unknown rounding method {method!r}")
+        return int(rounding_threshold_bits["n_bits"]), method
+    return int(rounding_threshold_bits), "exact"
 
 
 def compile_torch_model(torch_model: torch.nn.Module, torch_inputset, n_bits: Union[int, dict] = 8,
@@ -29,8 +30,9 @@ def compile_torch_model(torch_model: torch.nn.Module, torch_inputset, n_bits: Un
         n_bits = int(n_bits.get("op_inputs", n_bits.get("model_inputs", 8)))
     if isinstance(torch_inputset, np.ndarray):
         torch_inputset = torch.from_numpy(torch_inputset)
+    bits, method = _rounding(rounding_threshold_bits)
     return QuantizedModule.compile(torch_model, torch_inputset, n_bits=int(n_bits),
-                                   rounding_threshold_bits=_rounding_bits(rounding_threshold_bits),
+                                   rounding_threshold_bits=bits, rounding_method=method,
                                    p_error=0.01 if p_error is None else float(p_error), configuration=configuration,
                                    verbose=verbose)
 

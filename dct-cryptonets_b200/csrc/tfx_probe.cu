@@ -21,18 +21,20 @@ __global__ void __launch_bounds__(256) dfma_probe_kernel(double* out, int iters,
 }
 
 __global__ void __launch_bounds__(256) imac_probe_kernel(uint64_t* out, int iters, uint32_t d0) {
-    uint64_t a[8];
-    uint64_t k = 0x9E3779B97F4A7C15ull * (threadIdx.x + 1);
-    uint32_t d = d0 + threadIdx.x;
+    // same instruction pattern as the keyswitch inner product: lo64 += d * k_lo (IMAD.WIDE.U32), hi32 += d * k_hi (IMAD)
+    uint64_t lo[8]; uint32_t hi[8];
+    uint32_t klo = 0x9E3779B9u * (threadIdx.x + 1), khi = 0x7F4A7C15u ^ threadIdx.x;
+    uint32_t d = d0 + (threadIdx.x & 7);
 #pragma unroll
-    for (int j = 0; j < 8; j++) a[j] = j;
+    for (int j = 0; j < 8; j++) { lo[j] = j; hi[j] = j; }
     for (int i = 0; i < iters; i++) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) a[j] += (uint64_t)d * (k + a[(j + 1) & 7]);
+        for (int j = 0; j < 8; j++) { lo[j] += (uint64_t)d * klo; hi[j] += d * khi; }
+        klo += d; khi ^= klo;
     }
     uint64_t s = 0;
 #pragma unroll
-    for (int j = 0; j < 8; j++) s += a[j];
+    for (int j = 0; j < 8; j++) s += lo[j] + ((uint64_t)hi[j] << 32);
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 

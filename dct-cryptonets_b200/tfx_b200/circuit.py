@@ -103,6 +103,8 @@ class Circuit:
     n_bits: int
     rounding_bits: int
     p_error: float
+    rounding_method: str = "exact"   # "exact": bit-extraction chain; "approximate": the table lookup is applied
+                                     # to the unrounded accumulator, low bits ride inside the LUT box (reference README.md:96-113)
 
     # ---- statistics ------------------------------------------------------------------------------------
     def lookups(self) -> List[TluOp]:
@@ -110,7 +112,7 @@ class Circuit:
 
     def pbs_count(self) -> Dict[str, int]:
         tlu = sum(int(np.prod(op.shape)) for op in self.lookups())
-        bit = sum(int(np.prod(op.shape)) * op.lsbs for op in self.lookups())
+        bit = sum(int(np.prod(op.shape)) * op.lsbs for op in self.lookups()) if self.rounding_method == "exact" else 0
         return {"tlu": tlu, "bit": bit, "total": tlu + bit}
 
     def macs(self) -> int:
@@ -137,13 +139,18 @@ class Circuit:
             else:
                 norm2 = float(lin.sa ** 2 + lin.sb ** 2)
                 fresh = False
-            looks.append(RoundedLookup(op.acc_bits, op.keep_bits, max(norm2, 1.0), fresh, int(np.prod(op.shape))))
+            if self.rounding_method == "exact":
+                looks.append(RoundedLookup(op.acc_bits, op.keep_bits, max(norm2, 1.0), fresh, int(np.prod(op.shape))))
+            else:
+                # approximate: one t-bit lookup straight on the accumulator; the accumulator noise counts at the table's
+                # granularity (the low bits are signal that shifts the rounding threshold, not noise)
+                looks.append(RoundedLookup(op.keep_bits, op.keep_bits, max(norm2, 1.0), fresh, int(np.prod(op.shape))))
         return CircuitNoiseSpec(looks, self.p_error, input_std)
 
     def to_text(self) -> str:
         """Printable listing (plays the role of fhe_circuit.mlir, reference homomorphic_eval.py:311)."""
         lines = [f"circuit(input %{self.input_id}: eint<{self.input_width}>[{','.join(map(str, self.input_shape))}], "
-                 f"n_bits={self.n_bits}, rounding={self.rounding_bits}, p_error={self.p_error})"]
+                 f"n_bits={self.n_bits}, rounding={self.rounding_bits} ({self.rounding_method}), p_error={self.p_error})"]
         for op in self.ops:
             if op.kind == "conv":
                 k = "sum_pool" if op.depthwise else "conv2d"
@@ -510,5 +517,9 @@ def _bn_fn(m: nn.BatchNorm2d):
 
 
 def build_circuit(model: nn.Module, calib: torch.Tensor, n_bits: int = 5, rounding_threshold_bits: int = 6,
-                  p_error: float = 0.01, range_margin: float = 0.0) -> Circuit:
-    return CircuitBuilder(model, calib, n_bits, rounding_threshold_bits, p_error, range_margin).build()
+                  p_error: float = 0.01, range_margin: float = 0.0, rounding_method: str = "exact") -> Circuit:
+    if rounding_method not in ("exact", "approximate"):
+        raise ValueError("rounding_method must be 'exact' or 'approximate'")
+    circ = CircuitBuilder(model, calib, n_bits, rounding_threshold_bits, p_error, range_margin).build()
+    circ.rounding_method = rounding_method
+    return circ

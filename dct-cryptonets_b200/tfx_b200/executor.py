@@ -132,7 +132,11 @@ class CircuitExecutor:
         self._zero_idx = torch.zeros(max(int(np.prod(op.shape)) for op in self.circ.lookups()), dtype=torch.int32, device=dev)
 
     def _lsbs_after(self, lin_op) -> int:
-        """rounding bits removed by the lookup that consumes this accumulator (0 if it is the circuit output)"""
+        """rounding bits removed by the lookup that consumes this accumulator (0 if it is the circuit output).
+        Decides the half-LSB offset folded into the accumulator: in approximate mode the LUT's own half-box rotation
+        already rounds to nearest, so no offset is added."""
+        if self.circ.rounding_method != "exact":
+            return 0
         for op in self.circ.ops:
             if op.kind == "tlu" and op.src == lin_op.dst:
                 return op.lsbs
@@ -232,7 +236,7 @@ class CircuitExecutor:
                 nloc = acc.shape[0]
                 if nloc > 0:
                     w = op.acc_bits
-                    for b in range(op.lsbs):
+                    for b in range(op.lsbs if circ.rounding_method == "exact" else 0):
                         small = timed("ks_bit", nloc, lambda: keys.keyswitch(BIT_SET, acc, shift=w - b, body_offset=1 << 62))
                         lut, c = self._bit_luts[(w, b)]
                         timed("pbs_bit", nloc, lambda: keys.pbs(BIT_SET, small, lut, self._zero_idx[:nloc], mode=1, body_const=c, out=acc))
@@ -240,7 +244,8 @@ class CircuitExecutor:
                     out = timed("pbs_tlu", nloc, lambda: keys.pbs(TLU_SET, small, self._luts[op.dst],
                                                                   self._lut_index[op.dst][lo * H * W: hi * H * W]))
                     if stats is not None:
-                        stats.pbs_bit += nloc * op.lsbs; stats.pbs_tlu += nloc; stats.keyswitches += nloc * (op.lsbs + 1)
+                        nb = op.lsbs if circ.rounding_method == "exact" else 0
+                        stats.pbs_bit += nloc * nb; stats.pbs_tlu += nloc; stats.keyswitches += nloc * (nb + 1)
                 else:
                     out = ctx.empty_u64(0, words)
                 del acc

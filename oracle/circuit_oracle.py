@@ -80,7 +80,8 @@ def run_circuit(circ, keys: OracleKeys, in_cts: np.ndarray, collect: Optional[Di
     tlu_p, bit_p = keys.params[0], keys.params[1]
     words = in_cts.shape[-1]
     vals = {circ.input_id: in_cts.reshape(*circ.input_shape, words)}
-    lsbs_after = {op.src: op.lsbs for op in circ.ops if op.kind == "tlu"}
+    exact = getattr(circ, "rounding_method", "exact") == "exact"
+    lsbs_after = {op.src: op.lsbs for op in circ.ops if op.kind == "tlu"} if exact else {}
     t_lin = t_ks = t_pbs = 0.0
     for op in circ.ops:
         if op.kind == "conv":
@@ -101,7 +102,7 @@ def run_circuit(circ, keys: OracleKeys, in_cts: np.ndarray, collect: Optional[Di
             C, H, W = op.shape
             acc = np.ascontiguousarray(vals[op.src].reshape(-1, words)).copy()
             w = op.acc_bits
-            for b in range(op.lsbs):
+            for b in range(op.lsbs if exact else 0):
                 t0 = time.time()
                 small = O.keyswitch(keys.ksk[1], acc, bit_p.ksk_base_log, bit_p.ksk_level, shift=w - b, body_offset=1 << 62)
                 t1 = time.time()

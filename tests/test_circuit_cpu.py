@@ -143,8 +143,11 @@ def test_concrete_api_surface(tiny):
     assert y.shape == (3, 6) and np.array_equal(y, qm.forward(x, fhe="disable"))
     with pytest.raises(ValueError):
         qm.forward(x, fhe="bogus")
-    with pytest.raises(NotImplementedError):
-        compile_torch_model(m, calib, rounding_threshold_bits={"n_bits": 6, "method": "approximate"}, p_error=0.01, n_bits=5)
+    qa = compile_torch_model(m, calib, rounding_threshold_bits={"n_bits": 6, "method": "approximate"}, p_error=0.01, n_bits=5)
+    assert qa.fhe_circuit.statistics["bit"] == 0 and qa.fhe_circuit.statistics["tlu"] == qm.fhe_circuit.statistics["tlu"]
+    assert "approximate" in qa.fhe_circuit.mlir
+    with pytest.raises(ValueError):
+        compile_torch_model(m, calib, rounding_threshold_bits={"n_bits": 6, "method": "nearest"}, p_error=0.01, n_bits=5)
     qm2 = compile_brevitas_qat_model(m, calib, rounding_threshold_bits=6, n_bits=5, p_error=0.01, configuration=cfg)
     assert qm2.fhe_circuit.statistics["total"] == qm.fhe_circuit.statistics["total"]
     if not torch.cuda.is_available():

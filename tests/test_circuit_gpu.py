@@ -94,3 +94,28 @@ def test_client_server_deployment_roundtrip(gpu_ctx, tmp_path):
     y = client.deserialize_decrypt_dequantize(result)
     assert np.array_equal(y, qm.forward(x, fhe="simulate"))
     assert server._ex.keys is not client._ex.keys
+
+
+def test_approximate_rounding_matches_oracle_and_clear(gpu_ctx, oracle):
+    """rounding method 'approximate' (reference README.md:96-113): no bit-extraction chain, same table; with negligible
+    noise the thresholds are exact, so outputs equal the clear evaluator; ciphertexts equal the oracle's."""
+    from oracle import circuit_oracle as CO
+    torch.manual_seed(0)
+    model = TinyNet().eval()
+    calib = torch.randn(40, 3, 4, 4)
+    circ = C.build_circuit(model, calib, 5, 6, 0.01, rounding_method="approximate")
+    assert circ.pbs_count()["bit"] == 0
+    ex = CircuitExecutor(circ, (TOY_TLU, TOY_BIT), ctx=gpu_ctx, input_std=2.0**-50)
+    ex.keygen(seed=5)
+    q_in = C.quantize_input(circ, calib[:1].numpy())[0]
+    stats = RunStats()
+    out = ex.run(ex.encrypt(q_in, enc_seed=6), stats)
+    keys = CO.OracleKeys((TOY_TLU, TOY_BIT), 5)
+    ref = CO.run_circuit(circ, keys, CO.encrypt_input(circ, keys, q_in, 2.0**-50, 6))
+    assert np.array_equal(gpu_ctx.to_host_u64(out), ref), "GPU ciphertexts differ from the oracle's (approximate mode)"
+    assert stats.pbs_bit == 0 and stats.pbs_tlu == circ.pbs_count()["tlu"]
+    clear = C.evaluate_clear(circ, q_in[None])[0].astype(np.float64)
+    dec = ex.decrypt(out).reshape(clear.shape).astype(np.float64)
+    # approximate rounding: the mod-switch noise blurs every rounding threshold (that is the approximation), so the
+    # decrypted features track the clear evaluation without being equal to it
+    assert np.abs(dec - clear).max() <= 0.35 * max(1.0, np.abs(clear).max()), (dec, clear)
