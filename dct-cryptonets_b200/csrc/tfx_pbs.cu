@@ -47,6 +47,12 @@ struct PbsArgs {
 // lower levels (carry iff lower part >= thr[lvl]); identical to the sequential rule of decompose_digit().
 struct DigitCtx { uint64_t round_add; int top_shift; int base_log; uint64_t mask, half; };
 
+// single-level gadget: the balanced digit is the arithmetic top base_log bits of the rounded word
+__device__ __forceinline__ double digit1_as_double(uint64_t x, const DigitCtx& dc) {
+    const int64_t sd = (int64_t)(x + dc.round_add) >> dc.top_shift;
+    return __longlong_as_double(0x4338000000000000LL + sd) - 6755399441055744.0;
+}
+
 __device__ __forceinline__ double digit_as_double(uint64_t x, const DigitCtx& dc, int shift_in_top, uint64_t low_mask, uint64_t thr) {
     const uint64_t v = (x + dc.round_add) >> dc.top_shift;            // top base_log*level bits, rounded
     uint64_t d = (v >> shift_in_top) & dc.mask;
@@ -87,36 +93,70 @@ pbs_kernel(PbsArgs a) {
     }
     const int n_fwd = G * a.level;                 // forward transforms per CMux step, index f = r * level + lvl
 
-    // pass-0 input of forward transform f: digit polynomial (level f % level) of X^ahat * acc_r - acc_r, twisted
-    auto load_digits = [&](double2 (&x)[8], int f, uint32_t ahat) {
-        const int r = f / a.level, lvl = f - r * a.level;
-        const uint64_t* ar = acc + (size_t)r * N;
-        const int shift_in_top = a.base_log * (a.level - 1 - lvl);
-        const uint64_t low_mask = (shift_in_top > 0) ? ((1ULL << shift_in_top) - 1) : 0;
-        // carry threshold of the balanced representation of the m = level-1-lvl lower digits:
-        // (B/2 - 1) * (B^m - 1) / (B - 1) + 1  (== B/2 for m = 1); no lower digits -> never
-        uint64_t thr = ~0ULL;
+    // coefficient pair (j, j+M) of X^ahat * acc_r - acc_r
+    auto diff_pair = [&](const uint64_t* ar, int jc, uint32_t ahat, uint64_t& d0, uint64_t& d1) {
+        const uint32_t s0 = (uint32_t)(jc - (int)ahat) & (2 * N - 1);
+        const uint64_t r0 = s0 < N ? ar[s0] : (uint64_t)0 - ar[s0 - N];
+        d0 = r0 - ar[jc];
+        const uint32_t s1 = (s0 + M) & (2 * N - 1);
+        const uint64_t r1 = s1 < N ? ar[s1] : (uint64_t)0 - ar[s1 - N];
+        d1 = r1 - ar[jc + M];
+    };
+    // digit selector of level index lvl (0 = most significant): shift, low mask, carry threshold of the balanced
+    // representation of the m = level-1-lvl lower digits: (B/2 - 1) * (B^m - 1) / (B - 1) + 1 (== B/2 for m = 1)
+    auto level_sel = [&](int lvl, int& shift_in_top, uint64_t& low_mask, uint64_t& thr) {
+        shift_in_top = a.base_log * (a.level - 1 - lvl);
+        low_mask = (shift_in_top > 0) ? ((1ULL << shift_in_top) - 1) : 0;
+        thr = ~0ULL;
         if (shift_in_top > 0) {
             uint64_t rep = 0;
             for (int q = 0; q < a.level - 1 - lvl; q++) rep = (rep << a.base_log) | 1ULL;
             thr = (dc.half - 1) * rep + 1;
         }
+    };
+    // pass-0 input of forward transform f = r * level + lvl: digit polynomial of X^ahat * acc_r - acc_r, twisted
+    auto load_digits = [&](double2 (&x)[8], int f, uint32_t ahat) {
+        const int r = f / a.level, lvl = f - r * a.level;
+        const uint64_t* ar = acc + (size_t)r * N;
 #ifdef TFX_EXP_NODIGITS
         for (int e = 0; e < 8; e++) x[e] = make_double2((double)(t + e + f), (double)ahat);
         return;
 #endif
+        if (a.level == 1) {
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const int jc = t + e * TPF;
+                uint64_t d0, d1;
+                diff_pair(ar, jc, ahat, d0, d1);
+                x[e] = cmul(make_double2(digit1_as_double(d0, dc), digit1_as_double(d1, dc)), s_twist[jc]);
+            }
+            return;
+        }
+        int sh; uint64_t lm, thr;
+        level_sel(lvl, sh, lm, thr);
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const int jc = t + e * TPF;
-            const uint32_t s0 = (uint32_t)(jc - (int)ahat) & (2 * N - 1);
-            const uint64_t r0 = s0 < N ? ar[s0] : (uint64_t)0 - ar[s0 - N];
-            const uint64_t d0 = r0 - ar[jc];
-            const uint32_t s1 = (s0 + M) & (2 * N - 1);
-            const uint64_t r1 = s1 < N ? ar[s1] : (uint64_t)0 - ar[s1 - N];
-            const uint64_t d1 = r1 - ar[jc + M];
-            const double2 v = make_double2(digit_as_double(d0, dc, shift_in_top, low_mask, thr),
-                                           digit_as_double(d1, dc, shift_in_top, low_mask, thr));
-            x[e] = cmul(v, s_twist[jc]);
+            uint64_t d0, d1;
+            diff_pair(ar, jc, ahat, d0, d1);
+            x[e] = cmul(make_double2(digit_as_double(d0, dc, sh, lm, thr), digit_as_double(d1, dc, sh, lm, thr)), s_twist[jc]);
+        }
+    };
+    // two consecutive levels of the same component: the accumulator reads and the rotation are shared
+    auto load_digits_2levels = [&](double2 (&xa)[8], double2 (&xb)[8], int f, uint32_t ahat) {
+        const int r = f / a.level, lvl = f - r * a.level;
+        const uint64_t* ar = acc + (size_t)r * N;
+        int sha, shb; uint64_t lma, lmb, thra, thrb;
+        level_sel(lvl, sha, lma, thra);
+        level_sel(lvl + 1, shb, lmb, thrb);
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int jc = t + e * TPF;
+            uint64_t d0, d1;
+            diff_pair(ar, jc, ahat, d0, d1);
+            const double2 tws = s_twist[jc];
+            xa[e] = cmul(make_double2(digit_as_double(d0, dc, sha, lma, thra), digit_as_double(d1, dc, sha, lma, thra)), tws);
+            xb[e] = cmul(make_double2(digit_as_double(d0, dc, shb, lmb, thrb), digit_as_double(d1, dc, shb, lmb, thrb)), tws);
         }
     };
 
@@ -171,8 +211,12 @@ pbs_kernel(PbsArgs a) {
             for (int f = 0; f + 1 < n_fwd; f += 2) {
                 double2 xa[8], xb[8], w[7];
                 load_tw<LOGM, PassInfo<LOGM, 0>::LO, PassInfo<LOGM, 0>::WD>(w, t, s_tw);
-                load_digits(xa, f, ahat);
-                load_digits(xb, f + 1, ahat);
+                if ((a.level & 1) == 0) {                              // f even and level even: (f, f+1) are two levels of one component
+                    load_digits_2levels(xa, xb, f, ahat);
+                } else {
+                    load_digits(xa, f, ahat);
+                    load_digits(xb, f + 1, ahat);
+                }
                 fft_forward_regs2<LOGM, true>(xa, xb, w, t, bufa, bufb, s_tw, sync, wsync);
                 mac(xa, f);
                 mac(xb, f + 1);
