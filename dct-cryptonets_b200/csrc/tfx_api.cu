@@ -27,7 +27,8 @@ uint32_t ksk_npad(uint32_t n);
 int launch_ksk_repack(const uint64_t* src, uint64_t* dst, uint32_t rows, uint32_t n, int to_padded, cudaStream_t s);
 int launch_ksk_corr(const uint64_t* ksk_padded, uint64_t* corr, uint32_t rows, uint32_t n, int base_log, cudaStream_t s);
 
-// ---- host twiddle tables (definition shared with the parity contract: first octant from cosl/sinl, the rest by symmetry)
+// ---- host node-twiddle table of the negacyclic transform (definition: oracle/tfhe_oracle.c section 6): roots from
+//      cosl/sinl on the first octant, the other octants by exact symmetry
 static void unit_root(uint64_t num, uint64_t den, double* re, double* im) {
     const long double PI_L = 3.14159265358979323846264338327950288L;
     num %= den;
@@ -49,17 +50,46 @@ static void unit_root(uint64_t num, uint64_t den, double* re, double* im) {
     *im = sy[oct] > 0 ? y : -y;
 }
 
-static void make_tables(uint32_t N, std::vector<double>& twist, std::vector<double>& tw) {
-    const uint32_t M = N / 2;
-    twist.assign((size_t)M * 2, 0.0); tw.assign((size_t)M * 2, 0.0);
-    for (uint32_t j = 0; j < M; j++) unit_root(j, 2ULL * N, &twist[2 * j], &twist[2 * j + 1]);
-    for (uint32_t half = M / 2; half >= 1; half >>= 1) {
-        const uint32_t off = M - 2 * half;
-        for (uint32_t j = 0; j < half; j++) unit_root(j, 2ULL * half, &tw[2 * (off + j)], &tw[2 * (off + j) + 1]);
+static uint32_t bit_reverse(uint32_t v, int bits) {
+    uint32_t r = 0;
+    for (int i = 0; i < bits; i++) r |= ((v >> i) & 1u) << (bits - 1 - i);
+    return r;
+}
+
+// bits per pass for log2(M); must match FftPlan<> in tfx_common.cuh
+static int pass_plan(int logM, int wd[8]) {
+    switch (logM) {
+        case 8: wd[0] = 3; wd[1] = 3; wd[2] = 2; return 3;
+        case 9: wd[0] = 3; wd[1] = 3; wd[2] = 3; return 3;
+        case 10: wd[0] = 3; wd[1] = 2; wd[2] = 3; wd[3] = 2; return 4;
+        case 11: wd[0] = 3; wd[1] = 3; wd[2] = 3; wd[3] = 2; return 4;
+        case 12: wd[0] = 3; wd[1] = 3; wd[2] = 3; wd[3] = 3; return 4;
+        default: { int n = 0, left = logM; while (left >= 3) { wd[n++] = 3; left -= 3; } if (left) wd[n++] = left; return n; }
     }
 }
 
-struct FftTables { uint32_t N = 0; double* twist_d = nullptr; double* tw_d = nullptr; };
+// flat table: pass p, node h (S_p bits), power q = 1..R-1 at offset_p + h*(R-1) + q-1:
+//   rho^q = exp(i*2*pi * q*(1 + 4*bitrev(h)) / (R * 2^(S+2)))
+static void make_tables(uint32_t N, std::vector<double>& tw) {
+    const uint32_t M = N / 2;
+    int logM = 0; while ((1u << logM) < M) logM++;
+    tw.assign((size_t)M * 2, 0.0);
+    int wd[8];
+    const int np = pass_plan(logM, wd);
+    uint32_t off = 0; int done = 0;
+    for (int p = 0; p < np; p++) {
+        const int R = 1 << wd[p], S = done;
+        for (uint32_t h = 0; h < (1u << S); h++)
+            for (int q = 1; q < R; q++) {
+                const size_t idx = off + (size_t)h * (R - 1) + (q - 1);
+                unit_root((uint64_t)q * (1 + 4ULL * bit_reverse(h, S)), (uint64_t)R << (S + 2), &tw[2 * idx], &tw[2 * idx + 1]);
+            }
+        off += (1u << S) * (R - 1);
+        done += wd[p];
+    }
+}
+
+struct FftTables { uint32_t N = 0; double* tw_d = nullptr; };
 
 }  // namespace tfx
 
@@ -91,14 +121,12 @@ static int use_device(tfx_ctx* ctx) {
 
 static int get_tables(tfx_ctx* ctx, uint32_t N, FftTables** out) {
     for (auto& t : ctx->tables) if (t.N == N) { *out = &t; return TFX_OK; }
-    std::vector<double> twist, tw;
-    make_tables(N, twist, tw);
+    std::vector<double> tw;
+    make_tables(N, tw);
     FftTables t; t.N = N;
     const size_t bytes = (size_t)N / 2 * 16;
-    cudaError_t e = cudaMalloc(&t.twist_d, bytes); if (e != cudaSuccess) return set_cuda_error(e, "cudaMalloc(twist)");
-    e = cudaMalloc(&t.tw_d, bytes); if (e != cudaSuccess) return set_cuda_error(e, "cudaMalloc(tw)");
-    e = cudaMemcpyAsync(t.twist_d, twist.data(), bytes, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(t.tw_d, tw.data(), bytes, cudaMemcpyHostToDevice, ctx->stream);
+    cudaError_t e = cudaMalloc(&t.tw_d, bytes); if (e != cudaSuccess) return set_cuda_error(e, "cudaMalloc(tw)");
+    e = cudaMemcpyAsync(t.tw_d, tw.data(), bytes, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);       // host vectors die at scope exit
     if (e != cudaSuccess) return set_cuda_error(e, "upload fft tables");
     ctx->tables.push_back(t);
@@ -180,7 +208,7 @@ void tfx_ctx_destroy(tfx_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (auto& t : ctx->tables) { cudaFree(t.twist_d); cudaFree(t.tw_d); }
+    for (auto& t : ctx->tables) cudaFree(t.tw_d);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -249,7 +277,7 @@ int tfx_keyset_generate(tfx_ctx* ctx, uint32_t big_dim, const tfx_pbs_params* se
         rc = launch_gen_bsk(seed, s, k1.small_key_d, p.n, ks->big_key_d, p.k, p.N, p.bsk_base_log, p.bsk_level, p.glwe_std, std_d, st);
         FftTables* tb = nullptr;
         if (!rc) rc = get_tables(ctx, p.N, &tb);
-        if (!rc) rc = launch_fft(0, p.N, std_d, k1.bsk_d, tb->twist_d, tb->tw_d, bsk_polys(p), ctx->sm_count, st);
+        if (!rc) rc = launch_fft(0, p.N, std_d, k1.bsk_d, tb->tw_d, bsk_polys(p), ctx->sm_count, st);
         cudaError_t es = cudaStreamSynchronize(st);
         if (!rc && es != cudaSuccess) rc = set_cuda_error(es, "keygen");
         if (keep_standard_bsk && !rc) { k1.bsk_std_d = std_d; ks->bytes += bsk_doubles(p) * 8; } else cudaFree(std_d);
@@ -338,11 +366,11 @@ static int bsk_xfer(tfx_keyset* ks, uint32_t set, double* host, bool to_host) {
     double* tmp = nullptr;
     cudaError_t e = cudaMalloc(&tmp, bytes); if (e != cudaSuccess) return set_cuda_error(e, "cudaMalloc");
     if (to_host) {
-        rc = launch_fft(3, k1.p.N, k1.bsk_d, tmp, nullptr, nullptr, bsk_polys(k1.p), ks->ctx->sm_count, ks->ctx->stream);
+        rc = launch_fft(3, k1.p.N, k1.bsk_d, tmp, nullptr, bsk_polys(k1.p), ks->ctx->sm_count, ks->ctx->stream);
         if (!rc) rc = copy_sync(ks->ctx, host, tmp, bytes, cudaMemcpyDeviceToHost);
     } else {
         rc = copy_sync(ks->ctx, tmp, host, bytes, cudaMemcpyHostToDevice);
-        if (!rc) rc = launch_fft(4, k1.p.N, tmp, k1.bsk_d, nullptr, nullptr, bsk_polys(k1.p), ks->ctx->sm_count, ks->ctx->stream);
+        if (!rc) rc = launch_fft(4, k1.p.N, tmp, k1.bsk_d, nullptr, bsk_polys(k1.p), ks->ctx->sm_count, ks->ctx->stream);
         cudaStreamSynchronize(ks->ctx->stream);
     }
     cudaFree(tmp);
@@ -423,7 +451,7 @@ int tfx_pbs_batch(tfx_ctx* ctx, tfx_keyset* ks, uint32_t set, const uint64_t* in
     FftTables* tb = nullptr;
     rc = get_tables(ctx, k1.p.N, &tb); if (rc) return rc;
     PbsLaunch p;
-    p.bsk = k1.bsk_d; p.twist = tb->twist_d; p.tw = tb->tw_d; p.in = in_d; p.luts = luts_d; p.lut_index = lut_index_d; p.out = out_d;
+    p.bsk = k1.bsk_d; p.tw = tb->tw_d; p.in = in_d; p.luts = luts_d; p.lut_index = lut_index_d; p.out = out_d;
     p.n = k1.p.n; p.k = k1.p.k; p.N = k1.p.N; p.base_log = (int)k1.p.bsk_base_log; p.level = (int)k1.p.bsk_level;
     p.mode = mode; p.body_const = body_const; p.count = B; p.sm_count = ctx->sm_count;
     return launch_pbs(p, ctx->stream);
@@ -451,11 +479,10 @@ int tfx_probe_rate(tfx_ctx* ctx, int which, double* rate_out) {
     return probe_rate(which, ctx->sm_count, ctx->stream, rate_out);
 }
 
-int tfx_fft_tables(uint32_t N, double* twist_h, double* tw_h) {
-    if (!twist_h || !tw_h || N < 16 || (N & (N - 1))) return set_error(TFX_ERR_ARG, "fft_tables: bad argument");
-    std::vector<double> twist, tw;
-    make_tables(N, twist, tw);
-    memcpy(twist_h, twist.data(), twist.size() * 8);
+int tfx_fft_tables(uint32_t N, double* tw_h) {
+    if (!tw_h || N < 16 || (N & (N - 1))) return set_error(TFX_ERR_ARG, "fft_tables: bad argument");
+    std::vector<double> tw;
+    make_tables(N, tw);
     memcpy(tw_h, tw.data(), tw.size() * 8);
     return TFX_OK;
 }
@@ -465,7 +492,7 @@ int tfx_fft_forward(tfx_ctx* ctx, uint32_t N, const double* polys_d, size_t P, d
     int rc = use_device(ctx); if (rc) return rc;
     FftTables* tb = nullptr;
     rc = get_tables(ctx, N, &tb); if (rc) return rc;
-    return launch_fft(1, N, polys_d, freq_d, tb->twist_d, tb->tw_d, P, ctx->sm_count, ctx->stream);
+    return launch_fft(1, N, polys_d, freq_d, tb->tw_d, P, ctx->sm_count, ctx->stream);
 }
 
 int tfx_fft_inverse(tfx_ctx* ctx, uint32_t N, const double* freq_d, size_t P, uint64_t* torus_d) {
@@ -473,7 +500,7 @@ int tfx_fft_inverse(tfx_ctx* ctx, uint32_t N, const double* freq_d, size_t P, ui
     int rc = use_device(ctx); if (rc) return rc;
     FftTables* tb = nullptr;
     rc = get_tables(ctx, N, &tb); if (rc) return rc;
-    return launch_fft(2, N, freq_d, torus_d, tb->twist_d, tb->tw_d, P, ctx->sm_count, ctx->stream);
+    return launch_fft(2, N, freq_d, torus_d, tb->tw_d, P, ctx->sm_count, ctx->stream);
 }
 
 }  // extern "C"

@@ -1,7 +1,7 @@
 // tfx_common.cuh — device primitives shared by the TFHE kernels (sm_100a).
 // Floating point discipline: this library is compiled with -fmad=false; every fused multiply-add is an
-// explicit fma().  The butterfly dataflow is radix-2 (DIF forward / DIT inverse) regrouped into register
-// passes of 2-3 stages; regrouping does not change any floating-point operation.
+// explicit fma().  The transform dataflow (radix-8 / radix-4 nodes of the negacyclic factor tree) is defined by
+// oracle/tfhe_oracle.c section 6 and mirrored here operation for operation.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -157,9 +157,11 @@ __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_doub
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 
 // ------------------------------------------------------------------------------------------------
-// FFT plan: M = 2^LOGM complex points, TPF = M/8 threads, 8 points per thread per pass.
-// Pass p works on an index bit field of width WD[p] (2 or 3) whose lowest bit is LO[p].
-// Field layouts are chosen so the XOR swizzle below keeps every quarter-warp access conflict free.
+// Negacyclic transform (definition: oracle/tfhe_oracle.c section 6): z_j = p_j + i p_{j+M} evaluated at the roots of
+// X^M = i by a tree of radix-8 / radix-4 nodes, no separate twist.  M = 2^LOGM complex points, TPF = M/8 threads,
+// 8 points per thread per pass.  Pass p works on an index bit field of width WD[p] (2 or 3) whose lowest bit is
+// LO[p]; a 3-bit pass is one radix-8 node per thread, a 2-bit pass two radix-4 nodes.  Field layouts are chosen so
+// the XOR swizzle below keeps every quarter-warp access conflict free.
 // ------------------------------------------------------------------------------------------------
 template <int LOGM> struct FftPlan;
 template <> struct FftPlan<8>  { static constexpr int P = 3; static constexpr int WD[4] = {3, 3, 2, 0}; };
@@ -170,8 +172,15 @@ template <> struct FftPlan<12> { static constexpr int P = 4; static constexpr in
 
 template <int LOGM, int PASS> struct PassInfo {
     static constexpr int WD = FftPlan<LOGM>::WD[PASS];
-    static constexpr int lo_calc() { int s = 0; for (int q = 0; q <= PASS; q++) s += FftPlan<LOGM>::WD[q]; return LOGM - s; }
-    static constexpr int LO = lo_calc();
+    static constexpr int done_calc() { int s = 0; for (int q = 0; q < PASS; q++) s += FftPlan<LOGM>::WD[q]; return s; }
+    static constexpr int S = done_calc();                       // index bits already split off = bits of the node id h
+    static constexpr int LO = LOGM - S - WD;
+    static constexpr int off_calc() {                            // offset of this pass's twiddles in the flat table
+        int off = 0, done = 0;
+        for (int q = 0; q < PASS; q++) { off += (1 << done) * ((1 << FftPlan<LOGM>::WD[q]) - 1); done += FftPlan<LOGM>::WD[q]; }
+        return off;
+    }
+    static constexpr int OFF = off_calc();
 };
 
 __device__ __forceinline__ int swz(int idx) { return idx ^ ((idx >> 3) & 7); }
@@ -184,46 +193,10 @@ __device__ __forceinline__ int pass2_rest(int t, int u) { return ((t >> 5) << 6)
 // index (complex position in the M-array) of element e of thread t in a pass
 template <int LOGM, int LO, int WD>
 __device__ __forceinline__ int elem_index(int t, int e) {
-    constexpr int TPF = 1 << (LOGM - 3);
     int rest, f;
     if (WD == 3) { rest = t; f = e; }
     else { rest = pass2_rest(t, e >> 2); f = e & 3; }
-    (void)TPF;
     return ((rest >> LO) << (LO + WD)) | (f << LO) | (rest & ((1 << LO) - 1));
-}
-
-// radix-2 stages of one pass on the 8 register values.  tw: flat twiddle table (stage with half h at offset M-2h).
-template <int LOGM, int LO, int WD, bool INV>
-__device__ __forceinline__ void pass_butterflies(double2 (&x)[8], int t, const double2* __restrict__ tw) {
-    constexpr int M = 1 << LOGM;
-#pragma unroll
-    for (int q = 0; q < WD; q++) {
-        const int fb = INV ? q : (WD - 1 - q);            // field bit handled by this stage
-        const int half = 1 << (LO + fb);
-        const int off = M - 2 * half;
-#pragma unroll
-        for (int e = 0; e < 8; e++) {
-            const int f = (WD == 3) ? e : (e & 3);
-            if (f & (1 << fb)) continue;                    // e is the 'a' element of its pair
-            const int eb = e | (1 << fb);
-            if (half == 1) {
-                double2 a = x[e], b = x[eb];
-                x[e] = cadd(a, b); x[eb] = csub(a, b);
-            } else {
-                const int rest = (WD == 3) ? t : pass2_rest(t, e >> 2);
-                const int j = ((f & ((1 << fb) - 1)) << LO) | (rest & ((1 << LO) - 1));
-                const double2 w = tw[off + j];
-                if (!INV) {
-                    double2 a = x[e], b = x[eb];
-                    x[e] = cadd(a, b);
-                    x[eb] = cmul(csub(a, b), w);
-                } else {
-                    double2 a = x[e], b = cmulc(x[eb], w);
-                    x[e] = cadd(a, b); x[eb] = csub(a, b);
-                }
-            }
-        }
-    }
 }
 
 template <int LOGM, int PASS>
@@ -245,107 +218,114 @@ __device__ __forceinline__ void pass_load(double2 (&x)[8], int t, const double2*
     for (int e = 0; e < 8; e++) x[e] = buf[swz(elem_index<LOGM, PI::LO, PI::WD>(t, e))];
 }
 
-// Forward passes 1..P-1 given pass-0 INPUT values already in x (pass-0 element order: index = t + e*TPF).
-// On return x holds the frequency-domain values of the last pass's elements (index elem_index<LAST>(t, e)).
-// SYNC is a functor performing the barrier for the threads sharing `buf`.
-// SYNC_CTA orders the first (cross-warp) exchange, SYNC_WARP the later, warp-local ones.
-template <int LOGM, typename SYNC_CTA, typename SYNC_WARP>
-__device__ __forceinline__ void fft_forward_regs(double2 (&x)[8], int t, double2* __restrict__ buf,
-                                                 const double2* __restrict__ tw, SYNC_CTA sync, SYNC_WARP wsync) {
-    using PL = FftPlan<LOGM>;
-    pass_butterflies<LOGM, PassInfo<LOGM, 0>::LO, PassInfo<LOGM, 0>::WD, false>(x, t, tw);
-    pass_store<LOGM, 0>(x, t, buf);
-    sync();
-    pass_load<LOGM, 1>(x, t, buf);
-    pass_butterflies<LOGM, PassInfo<LOGM, 1>::LO, PassInfo<LOGM, 1>::WD, false>(x, t, tw);
-    if constexpr (PL::P >= 3) {
-        pass_store<LOGM, 1>(x, t, buf);                 // in place: a thread rewrites exactly the elements it loaded
-        wsync();
-        pass_load<LOGM, 2>(x, t, buf);
-        pass_butterflies<LOGM, PassInfo<LOGM, 2>::LO, PassInfo<LOGM, 2>::WD, false>(x, t, tw);
-    }
-    if constexpr (PL::P >= 4) {
-        pass_store<LOGM, 2>(x, t, buf);
-        wsync();
-        pass_load<LOGM, 3>(x, t, buf);
-        pass_butterflies<LOGM, PassInfo<LOGM, 3>::LO, PassInfo<LOGM, 3>::WD, false>(x, t, tw);
-    }
-}
-template <int LOGM, typename SYNC>
-__device__ __forceinline__ void fft_forward_regs(double2 (&x)[8], int t, double2* __restrict__ buf,
-                                                 const double2* __restrict__ tw, SYNC sync) {
-    fft_forward_regs<LOGM>(x, t, buf, tw, sync, sync);
-}
-
-// ---- twiddles of a pass preloaded into registers (issued before the preceding barrier so their shared-memory
-//      latency overlaps the barrier wait and the data loads) ----------------------------------------------------
-// slot layout: stage with field bit fb uses slots [(1 << WD) - (2 << fb), ...) indexed by the low fb bits of f
-template <int WD> struct TwSlots { static constexpr int N = (1 << WD) - 1; };
-
-template <int LOGM, int LO, int WD>
+// node twiddles rho^q (q = 1..R-1) of the thread's node(s) in pass PASS: w[0..6] (radix 8) or w[0..2], w[3..5] (two radix-4)
+template <int LOGM, int PASS>
 __device__ __forceinline__ void load_tw(double2 (&w)[7], int t, const double2* __restrict__ tw) {
-    constexpr int M = 1 << LOGM;
-    const int rest_lo = ((WD == 3) ? t : pass2_rest(t, 0)) & ((1 << LO) - 1);
+    using PI = PassInfo<LOGM, PASS>;
+    if (PI::WD == 3) {
+        const double2* p = tw + PI::OFF + (t >> PI::LO) * 7;
 #pragma unroll
-    for (int fb = WD - 1; fb >= 0; fb--) {
-        const int half = 1 << (LO + fb);
-        if (half == 1) continue;
-        const int off = M - 2 * half;
-        const int base = (1 << WD) - (2 << fb);
+        for (int q = 0; q < 7; q++) w[q] = p[q];
+    } else {
 #pragma unroll
-        for (int fl = 0; fl < (1 << fb); fl++) {
-            if (LO == 0 && (fl == 0 || 2 * fl == half)) continue;           // exactly 1 and i: handled without a multiply
-            w[base + fl] = tw[off + ((fl << LO) | rest_lo)];
+        for (int u = 0; u < 2; u++) {
+            const double2* p = tw + PI::OFF + (pass2_rest(t, u) >> PI::LO) * 3;
+#pragma unroll
+            for (int q = 0; q < 3; q++) w[u * 3 + q] = p[q];
         }
     }
 }
 
-template <int LOGM, int LO, int WD, bool INV>
-__device__ __forceinline__ void pass_butterflies_w(double2 (&x)[8], const double2 (&w)[7]) {
+#define TFX_SQRT_HALF 0.70710678118654757
+__device__ __forceinline__ double2 mul_i(double2 a) { return make_double2(-a.y, a.x); }
+__device__ __forceinline__ double2 mul_mi(double2 a) { return make_double2(a.y, -a.x); }
+__device__ __forceinline__ double2 mul_w8(double2 a) { return make_double2(TFX_SQRT_HALF * (a.x - a.y), TFX_SQRT_HALF * (a.x + a.y)); }
+__device__ __forceinline__ double2 mul_w83(double2 a) { return make_double2(-(TFX_SQRT_HALF * (a.x + a.y)), TFX_SQRT_HALF * (a.x - a.y)); }
+__device__ __forceinline__ double2 mul_w8c(double2 a) { return make_double2(TFX_SQRT_HALF * (a.x + a.y), TFX_SQRT_HALF * (a.y - a.x)); }
+__device__ __forceinline__ double2 mul_w83c(double2 a) { return make_double2(TFX_SQRT_HALF * (a.y - a.x), -(TFX_SQRT_HALF * (a.x + a.y))); }
+
+// forward radix-R node on y[B .. B+R) (B = 0 or 4): premultiply by rho^q, then the constant-twiddle DIF network
+template <int WD, int B>
+__device__ __forceinline__ void node_forward(double2 (&y)[8], const double2 (&w)[7], int wbase) {
+    constexpr int R = 1 << WD;
+#pragma unroll
+    for (int q = 1; q < R; q++) y[B + q] = cmul(y[B + q], w[wbase + q - 1]);
+    if (WD == 3) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const double2 a = y[B + q], b = y[B + q + 4], d = csub(a, b);
+            y[B + q] = cadd(a, b);
+            y[B + q + 4] = (q == 0) ? d : (q == 1) ? mul_w8(d) : (q == 2) ? mul_i(d) : mul_w83(d);
+        }
+    }
+#pragma unroll
+    for (int base = 0; base < R; base += 4)
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const double2 a = y[B + base + q], b = y[B + base + q + 2], d = csub(a, b);
+            y[B + base + q] = cadd(a, b);
+            y[B + base + q + 2] = (q == 0) ? d : mul_i(d);
+        }
+#pragma unroll
+    for (int base = 0; base < R; base += 2) {
+        const double2 a = y[B + base], b = y[B + base + 1];
+        y[B + base] = cadd(a, b); y[B + base + 1] = csub(a, b);
+    }
+}
+
+template <int WD, int B>
+__device__ __forceinline__ void node_inverse(double2 (&y)[8], const double2 (&w)[7], int wbase) {
+    constexpr int R = 1 << WD;
+#pragma unroll
+    for (int base = 0; base < R; base += 2) {
+        const double2 a = y[B + base], b = y[B + base + 1];
+        y[B + base] = cadd(a, b); y[B + base + 1] = csub(a, b);
+    }
+#pragma unroll
+    for (int base = 0; base < R; base += 4)
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const double2 a = y[B + base + q];
+            double2 b = y[B + base + q + 2];
+            if (q == 1) b = mul_mi(b);
+            y[B + base + q] = cadd(a, b); y[B + base + q + 2] = csub(a, b);
+        }
+    if (WD == 3) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const double2 a = y[B + q];
+            double2 b = y[B + q + 4];
+            b = (q == 0) ? b : (q == 1) ? mul_w8c(b) : (q == 2) ? mul_mi(b) : mul_w83c(b);
+            y[B + q] = cadd(a, b); y[B + q + 4] = csub(a, b);
+        }
+    }
+#pragma unroll
+    for (int q = 1; q < R; q++) y[B + q] = cmulc(y[B + q], w[wbase + q - 1]);
+}
+
+template <int LOGM, int PASS, bool INV>
+__device__ __forceinline__ void pass_nodes(double2 (&x)[8], const double2 (&w)[7]) {
 #ifdef TFX_EXP_NOMATH
     return;
 #endif
-#pragma unroll
-    for (int q = 0; q < WD; q++) {
-        const int fb = INV ? q : (WD - 1 - q);
-        const int half = 1 << (LO + fb);
-        const int base = (1 << WD) - (2 << fb);
-#pragma unroll
-        for (int e = 0; e < 8; e++) {
-            const int f = (WD == 3) ? e : (e & 3);
-            if (f & (1 << fb)) continue;
-            const int eb = e | (1 << fb);
-            const int fl = f & ((1 << fb) - 1);
-            const bool is_one = (half == 1) || (LO == 0 && fl == 0);
-            const bool is_i = (half != 1) && (LO == 0) && (2 * fl == half);
-            if (!INV) {
-                const double2 a = x[e], b = x[eb];
-                x[e] = cadd(a, b);
-                const double2 d = csub(a, b);
-                if (is_one) x[eb] = d;
-                else if (is_i) x[eb] = make_double2(-d.y, d.x);              // d * i
-                else x[eb] = cmul(d, w[base + fl]);
-            } else {
-                double2 b = x[eb];
-                if (is_one) {}
-                else if (is_i) b = make_double2(b.y, -b.x);                  // b * conj(i)
-                else b = cmulc(b, w[base + fl]);
-                const double2 a = x[e];
-                x[e] = cadd(a, b); x[eb] = csub(a, b);
-            }
-        }
+    constexpr int WD = PassInfo<LOGM, PASS>::WD;
+    if (WD == 3) {
+        if (!INV) node_forward<3, 0>(x, w, 0); else node_inverse<3, 0>(x, w, 0);
+    } else {
+        if (!INV) { node_forward<2, 0>(x, w, 0); node_forward<2, 4>(x, w, 3); }
+        else { node_inverse<2, 0>(x, w, 0); node_inverse<2, 4>(x, w, 3); }
     }
 }
 
-// ---- two transforms interleaved in one thread (independent instruction streams hide shared-memory latency) ----
-#define TFX_TW(P) load_tw<LOGM, PassInfo<LOGM, P>::LO, PassInfo<LOGM, P>::WD>(w, t, tw);
-#define TFX_PASS2(P, INV) \
-    pass_butterflies_w<LOGM, PassInfo<LOGM, P>::LO, PassInfo<LOGM, P>::WD, INV>(xa, w); \
-    if (DUAL) pass_butterflies_w<LOGM, PassInfo<LOGM, P>::LO, PassInfo<LOGM, P>::WD, INV>(xb, w);
+// ---- one or two transforms interleaved in one thread; twiddles of the next pass are loaded before the barrier ----
+#define TFX_TW(P) load_tw<LOGM, P>(w, t, tw);
+#define TFX_PASS2(P, INV) pass_nodes<LOGM, P, INV>(xa, w); if (DUAL) pass_nodes<LOGM, P, INV>(xb, w);
 #define TFX_STORE2(P) pass_store<LOGM, P>(xa, t, bufa); if (DUAL) pass_store<LOGM, P>(xb, t, bufb);
 #define TFX_LOAD2(P) pass_load<LOGM, P>(xa, t, bufa); if (DUAL) pass_load<LOGM, P>(xb, t, bufb);
 
-// forward: xa/xb hold pass-0 inputs, w the pass-0 twiddles (load_tw<.., pass 0>); on return xa/xb hold the spectra
+// forward: xa/xb hold pass-0 inputs (element e of thread t = index t + e*TPF), w the pass-0 twiddles;
+// on return xa/xb hold the spectra in the last pass's element order.  SYNC_CTA orders the first (cross-warp)
+// exchange and protects the buffers' previous contents, SYNC_WARP the later, warp-local exchanges.
 template <int LOGM, bool DUAL, typename SYNC_CTA, typename SYNC_WARP>
 __device__ __forceinline__ void fft_forward_regs2(double2 (&xa)[8], double2 (&xb)[8], double2 (&w)[7], int t,
                                                   double2* __restrict__ bufa, double2* __restrict__ bufb,
@@ -374,7 +354,7 @@ __device__ __forceinline__ void fft_forward_regs2(double2 (&xa)[8], double2 (&xb
     }
 }
 
-// inverse: xa/xb hold spectra (last-pass element order); on return pass-0 elements before untwist / scaling
+// inverse (no 1/M factor): xa/xb hold spectra (last-pass element order); on return element e = index t + e*TPF
 template <int LOGM, bool DUAL, typename SYNC_CTA, typename SYNC_WARP>
 __device__ __forceinline__ void fft_inverse_regs2(double2 (&xa)[8], double2 (&xb)[8], int t, double2* __restrict__ bufa,
                                                   double2* __restrict__ bufb, const double2* __restrict__ tw,
@@ -408,54 +388,7 @@ __device__ __forceinline__ void fft_inverse_regs2(double2 (&xa)[8], double2 (&xb
 #undef TFX_STORE2
 #undef TFX_LOAD2
 
-// Inverse: x holds last-pass elements in the frequency domain; on return x holds pass-0 elements
-// (index t + e*TPF) BEFORE the untwist / 1/M scaling.
-template <int LOGM, typename SYNC>
-__device__ __forceinline__ void fft_inverse_regs(double2 (&x)[8], int t, double2* __restrict__ buf,
-                                                 const double2* __restrict__ tw, SYNC sync) {
-    using PL = FftPlan<LOGM>;
-    if constexpr (PL::P >= 4) {
-        pass_butterflies<LOGM, PassInfo<LOGM, 3>::LO, PassInfo<LOGM, 3>::WD, true>(x, t, tw);
-        pass_store<LOGM, 3>(x, t, buf);
-        sync();
-        pass_load<LOGM, 2>(x, t, buf);
-    }
-    if constexpr (PL::P >= 3) {
-        pass_butterflies<LOGM, PassInfo<LOGM, 2>::LO, PassInfo<LOGM, 2>::WD, true>(x, t, tw);
-        pass_store<LOGM, 2>(x, t, buf);
-        sync();
-        pass_load<LOGM, 1>(x, t, buf);
-    }
-    pass_butterflies<LOGM, PassInfo<LOGM, 1>::LO, PassInfo<LOGM, 1>::WD, true>(x, t, tw);
-    pass_store<LOGM, 1>(x, t, buf);
-    sync();
-    pass_load<LOGM, 0>(x, t, buf);
-    pass_butterflies<LOGM, PassInfo<LOGM, 0>::LO, PassInfo<LOGM, 0>::WD, true>(x, t, tw);
-}
-
-// Inverse transform after the caller has run the LAST pass's butterflies from registers and stored them:
-// loads the next pass and finishes; on return x holds pass-0 elements before untwist / scaling.
-// Precondition: the last pass's values were stored and a warp-level sync done.  Warp-local passes use wsync,
-// the final cross-warp exchange uses sync.
-template <int LOGM, typename SYNC_CTA, typename SYNC_WARP>
-__device__ __forceinline__ void fft_inverse_tail(double2 (&x)[8], int t, double2* __restrict__ buf,
-                                                 const double2* __restrict__ tw, SYNC_CTA sync, SYNC_WARP wsync) {
-    using PL = FftPlan<LOGM>;
-    if constexpr (PL::P >= 4) {
-        pass_load<LOGM, 2>(x, t, buf);
-        pass_butterflies<LOGM, PassInfo<LOGM, 2>::LO, PassInfo<LOGM, 2>::WD, true>(x, t, tw);
-        pass_store<LOGM, 2>(x, t, buf);
-        wsync();
-    }
-    pass_load<LOGM, 1>(x, t, buf);
-    pass_butterflies<LOGM, PassInfo<LOGM, 1>::LO, PassInfo<LOGM, 1>::WD, true>(x, t, tw);
-    pass_store<LOGM, 1>(x, t, buf);
-    sync();
-    pass_load<LOGM, 0>(x, t, buf);
-    pass_butterflies<LOGM, PassInfo<LOGM, 0>::LO, PassInfo<LOGM, 0>::WD, true>(x, t, tw);
-}
-
-// canonical FFT position of element e of thread t after the last forward pass
+// canonical transform position of element e of thread t after the last forward pass
 template <int LOGM>
 __device__ __forceinline__ int last_pass_index(int t, int e) {
     constexpr int LAST = FftPlan<LOGM>::P - 1;

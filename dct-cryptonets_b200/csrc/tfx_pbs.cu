@@ -4,7 +4,7 @@
 // One CTA (M/8 threads, 8 complex points per thread) owns one ciphertext at a time (grid-stride over the
 // batch); two CTAs share an SM for N <= 2048.  The GLWE accumulator ((k+1) x N torus words) lives in shared memory
 // for the whole blind rotation.  Per CMux step the CTA runs, for every accumulator component r and gadget level,
-// the forward FFT of the digit polynomial (rotation, decomposition and twist fused into the first register pass),
+// the forward FFT of the digit polynomial (rotation and decomposition fused into the first register pass; the transform needs no twist),
 // multiplies the spectrum with the Fourier bootstrapping-key rows (r, lvl, *) streamed from HBM/L2 in a
 // thread-major layout (coalesced 16 B per lane) and accumulates the (k+1) output spectra in registers; then the
 // (k+1) inverse FFTs run from those registers and add the rounded result into the accumulator.
@@ -22,17 +22,16 @@ template <int LOGN, int K> struct PbsCfg {
     static constexpr int TPF = M / 8;                    // threads per ciphertext (8 complex points each)
     static constexpr int G = K + 1;
     static constexpr int THREADS = TPF;
-    // accumulator + two FFT buffers (alternating per transform) + twiddle and twist tables
+    // accumulator + two transform buffers (one per interleaved transform) + node twiddle table
     static constexpr size_t smem_bytes(int) {
-        return (size_t)G * N * 8 + (size_t)M * 16 * 2 + (size_t)M * 16 * 2;
+        return (size_t)G * N * 8 + (size_t)M * 16 * 2 + (size_t)M * 16;
     }
     static constexpr int MIN_BLOCKS = (LOGN <= 11) ? 2 : 1;
 };
 
 struct PbsArgs {
     const double2* bsk;        // [n][G][l][G][8][TPF]
-    const double2* twist;      // [M]
-    const double2* tw;         // [M]
+    const double2* tw;         // [M] node twiddles, flat per pass
     const uint64_t* in;        // [B][n+1]
     const uint64_t* luts;      // [T][N]
     const uint32_t* lut_index; // [B]
@@ -72,7 +71,6 @@ pbs_kernel(PbsArgs a) {
     uint64_t* acc = reinterpret_cast<uint64_t*>(smem_raw);                    // [G][N]
     double2* bufs = reinterpret_cast<double2*>(acc + (size_t)G * N);          // [2][M] swizzled, alternate per transform
     double2* s_tw = bufs + 2 * M;                                             // [M]
-    double2* s_twist = s_tw + M;                                              // [M]
 
     const int t = threadIdx.x;
     auto sync = [] { __syncthreads(); };
@@ -80,7 +78,7 @@ pbs_kernel(PbsArgs a) {
     double2* bufa = bufs;
     double2* bufb = bufs + M;
 
-    for (int i = t; i < M; i += TPF) { s_tw[i] = a.tw[i]; s_twist[i] = a.twist[i]; }
+    for (int i = t; i < M; i += TPF) s_tw[i] = a.tw[i];
 
     DigitCtx dc;
     {
@@ -114,7 +112,7 @@ pbs_kernel(PbsArgs a) {
             thr = (dc.half - 1) * rep + 1;
         }
     };
-    // pass-0 input of forward transform f = r * level + lvl: digit polynomial of X^ahat * acc_r - acc_r, twisted
+    // pass-0 input of forward transform f = r * level + lvl: digit polynomial of X^ahat * acc_r - acc_r
     auto load_digits = [&](double2 (&x)[8], int f, uint32_t ahat) {
         const int r = f / a.level, lvl = f - r * a.level;
         const uint64_t* ar = acc + (size_t)r * N;
@@ -128,7 +126,7 @@ pbs_kernel(PbsArgs a) {
                 const int jc = t + e * TPF;
                 uint64_t d0, d1;
                 diff_pair(ar, jc, ahat, d0, d1);
-                x[e] = cmul(make_double2(digit1_as_double(d0, dc), digit1_as_double(d1, dc)), s_twist[jc]);
+                x[e] = make_double2(digit1_as_double(d0, dc), digit1_as_double(d1, dc));
             }
             return;
         }
@@ -139,7 +137,7 @@ pbs_kernel(PbsArgs a) {
             const int jc = t + e * TPF;
             uint64_t d0, d1;
             diff_pair(ar, jc, ahat, d0, d1);
-            x[e] = cmul(make_double2(digit_as_double(d0, dc, sh, lm, thr), digit_as_double(d1, dc, sh, lm, thr)), s_twist[jc]);
+            x[e] = make_double2(digit_as_double(d0, dc, sh, lm, thr), digit_as_double(d1, dc, sh, lm, thr));
         }
     };
     // two consecutive levels of the same component: the accumulator reads and the rotation are shared
@@ -154,9 +152,8 @@ pbs_kernel(PbsArgs a) {
             const int jc = t + e * TPF;
             uint64_t d0, d1;
             diff_pair(ar, jc, ahat, d0, d1);
-            const double2 tws = s_twist[jc];
-            xa[e] = cmul(make_double2(digit_as_double(d0, dc, sha, lma, thra), digit_as_double(d1, dc, sha, lma, thra)), tws);
-            xb[e] = cmul(make_double2(digit_as_double(d0, dc, shb, lmb, thrb), digit_as_double(d1, dc, shb, lmb, thrb)), tws);
+            xa[e] = make_double2(digit_as_double(d0, dc, sha, lma, thra), digit_as_double(d1, dc, sha, lma, thra));
+            xb[e] = make_double2(digit_as_double(d0, dc, shb, lmb, thrb), digit_as_double(d1, dc, shb, lmb, thrb));
         }
     };
 
@@ -210,7 +207,7 @@ pbs_kernel(PbsArgs a) {
 #pragma unroll 1
             for (int f = 0; f + 1 < n_fwd; f += 2) {
                 double2 xa[8], xb[8], w[7];
-                load_tw<LOGM, PassInfo<LOGM, 0>::LO, PassInfo<LOGM, 0>::WD>(w, t, s_tw);
+                load_tw<LOGM, 0>(w, t, s_tw);
                 if ((a.level & 1) == 0) {                              // f even and level even: (f, f+1) are two levels of one component
                     load_digits_2levels(xa, xb, f, ahat);
                 } else {
@@ -223,7 +220,7 @@ pbs_kernel(PbsArgs a) {
             }
             if (n_fwd & 1) {
                 double2 xa[8], w[7];
-                load_tw<LOGM, PassInfo<LOGM, 0>::LO, PassInfo<LOGM, 0>::WD>(w, t, s_tw);
+                load_tw<LOGM, 0>(w, t, s_tw);
                 load_digits(xa, n_fwd - 1, ahat);
                 fft_forward_regs2<LOGM, false>(xa, xa, w, t, bufa, bufb, s_tw, sync, wsync);
                 mac(xa, n_fwd - 1);
@@ -237,10 +234,9 @@ pbs_kernel(PbsArgs a) {
 #endif
 #pragma unroll
                 for (int e = 0; e < 8; e++) {
-                    const int jc = t + e * TPF;
-                    const double2 rr = cmulc(x[e], s_twist[jc]);
-                    ac[jc] += double_to_torus(rr.x * (1.0 / M));
-                    ac[jc + M] += double_to_torus(rr.y * (1.0 / M));
+                    const int jc = t + e * TPF;                          // the key carries the 1/M of the inverse transform
+                    ac[jc] += double_to_torus(x[e].x);
+                    ac[jc + M] += double_to_torus(x[e].y);
                 }
             };
             // inverse transforms, two output components at a time
@@ -280,12 +276,11 @@ pbs_kernel(PbsArgs a) {
 
 // ---------------------------------------------------------------------------------------------------
 // Plain transforms: one group of TPF threads per polynomial.  MODE 0: u64 (signed) input -> thread-major
-// Fourier layout (BSK conversion).  MODE 1: double input -> canonical order (test hook).
+// spectrum scaled by 1/M (BSK conversion).  MODE 1: double input -> canonical order, unscaled (test hook).
 // ---------------------------------------------------------------------------------------------------
 template <int LOGN, int MODE>
 __global__ void __launch_bounds__(1 << (LOGN - 4))
-fft_forward_kernel(const void* __restrict__ in, double2* __restrict__ out, const double2* __restrict__ twist,
-                   const double2* __restrict__ tw, size_t polys) {
+fft_forward_kernel(const void* __restrict__ in, double2* __restrict__ out, const double2* __restrict__ tw, size_t polys) {
     constexpr int N = 1 << LOGN, M = N / 2, LOGM = LOGN - 1, TPF = M / 8;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* buf = reinterpret_cast<double2*>(smem_raw);
@@ -295,34 +290,33 @@ fft_forward_kernel(const void* __restrict__ in, double2* __restrict__ out, const
     auto sync = [] { __syncthreads(); };
     for (size_t p = blockIdx.x; p < polys; p += gridDim.x) {
         __syncthreads();
-        double2 x[8];
+        double2 x[8], w[7];
+        load_tw<LOGM, 0>(w, t, s_tw);
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const int jc = t + e * TPF;
-            double2 v;
             if (MODE == 0) {
                 const uint64_t* src = reinterpret_cast<const uint64_t*>(in) + p * N;
-                v = make_double2((double)(int64_t)src[jc], (double)(int64_t)src[jc + M]);
+                x[e] = make_double2((double)(int64_t)src[jc], (double)(int64_t)src[jc + M]);
             } else {
                 const double* src = reinterpret_cast<const double*>(in) + p * N;
-                v = make_double2(src[jc], src[jc + M]);
+                x[e] = make_double2(src[jc], src[jc + M]);
             }
-            x[e] = cmul(v, twist[jc]);
         }
-        fft_forward_regs<LOGM>(x, t, buf, s_tw, sync);
+        fft_forward_regs2<LOGM, false>(x, x, w, t, buf, buf, s_tw, sync, sync);
         double2* dst = out + p * M;
 #pragma unroll
         for (int e = 0; e < 8; e++) {
-            if (MODE == 0) dst[e * TPF + t] = x[e];
+            if (MODE == 0) dst[e * TPF + t] = make_double2(x[e].x * (1.0 / M), x[e].y * (1.0 / M));
             else dst[last_pass_index<LOGM>(t, e)] = x[e];
         }
     }
 }
 
+// canonical spectrum -> torus polynomial: inverse transform, exact 1/M, round (test hook)
 template <int LOGN>
 __global__ void __launch_bounds__(1 << (LOGN - 4))
-fft_inverse_kernel(const double2* __restrict__ in, uint64_t* __restrict__ out, const double2* __restrict__ twist,
-                   const double2* __restrict__ tw, size_t polys) {
+fft_inverse_kernel(const double2* __restrict__ in, uint64_t* __restrict__ out, const double2* __restrict__ tw, size_t polys) {
     constexpr int N = 1 << LOGN, M = N / 2, LOGM = LOGN - 1, TPF = M / 8;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* buf = reinterpret_cast<double2*>(smem_raw);
@@ -336,14 +330,13 @@ fft_inverse_kernel(const double2* __restrict__ in, uint64_t* __restrict__ out, c
         const double2* src = in + p * M;
 #pragma unroll
         for (int e = 0; e < 8; e++) x[e] = src[last_pass_index<LOGM>(t, e)];
-        fft_inverse_regs<LOGM>(x, t, buf, s_tw, sync);
+        fft_inverse_regs2<LOGM, false>(x, x, t, buf, buf, s_tw, sync, sync);
         uint64_t* dst = out + p * N;
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const int jc = t + e * TPF;
-            double2 r = cmulc(x[e], twist[jc]);
-            dst[jc] = double_to_torus(r.x * (1.0 / M));
-            dst[jc + M] = double_to_torus(r.y * (1.0 / M));
+            dst[jc] = double_to_torus(x[e].x * (1.0 / M));
+            dst[jc + M] = double_to_torus(x[e].y * (1.0 / M));
         }
     }
 }
@@ -396,7 +389,7 @@ int pbs_supported(uint32_t N, uint32_t k) {
 
 int launch_pbs(const PbsLaunch& p, cudaStream_t stream) {
     PbsArgs a;
-    a.bsk = reinterpret_cast<const double2*>(p.bsk); a.twist = reinterpret_cast<const double2*>(p.twist);
+    a.bsk = reinterpret_cast<const double2*>(p.bsk);
     a.tw = reinterpret_cast<const double2*>(p.tw);
     a.in = p.in; a.luts = p.luts; a.lut_index = p.lut_index; a.out = p.out;
     a.n = p.n; a.base_log = p.base_log; a.level = p.level; a.mode = p.mode; a.body_const = p.body_const;
@@ -409,28 +402,27 @@ int launch_pbs(const PbsLaunch& p, cudaStream_t stream) {
 }
 
 template <int LOGN>
-static int launch_fft_t(int which, const void* in, void* out, const double* twist, const double* tw, size_t polys,
+static int launch_fft_t(int which, const void* in, void* out, const double* tw, size_t polys,
                         int sm_count, cudaStream_t stream) {
     constexpr int M = 1 << (LOGN - 1), TPF = M / 8;
     size_t smem = (size_t)M * 16 * 2;
     unsigned grid = (unsigned)(polys < (size_t)sm_count * 8 ? polys : (size_t)sm_count * 8);
     if (grid == 0) return TFX_OK;
-    const double2* tws = reinterpret_cast<const double2*>(twist);
     const double2* twd = reinterpret_cast<const double2*>(tw);
     cudaError_t e;
     if (which == 0) {
         e = cudaFuncSetAttribute(fft_forward_kernel<LOGN, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_cuda_error(e, "attr");
-        fft_forward_kernel<LOGN, 0><<<grid, TPF, smem, stream>>>(in, reinterpret_cast<double2*>(out), tws, twd, polys);
+        fft_forward_kernel<LOGN, 0><<<grid, TPF, smem, stream>>>(in, reinterpret_cast<double2*>(out), twd, polys);
     } else if (which == 1) {
         e = cudaFuncSetAttribute(fft_forward_kernel<LOGN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_cuda_error(e, "attr");
-        fft_forward_kernel<LOGN, 1><<<grid, TPF, smem, stream>>>(in, reinterpret_cast<double2*>(out), tws, twd, polys);
+        fft_forward_kernel<LOGN, 1><<<grid, TPF, smem, stream>>>(in, reinterpret_cast<double2*>(out), twd, polys);
     } else if (which == 2) {
         e = cudaFuncSetAttribute(fft_inverse_kernel<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_cuda_error(e, "attr");
         fft_inverse_kernel<LOGN><<<grid, TPF, smem, stream>>>(reinterpret_cast<const double2*>(in),
-                                                                reinterpret_cast<uint64_t*>(out), tws, twd, polys);
+                                                                reinterpret_cast<uint64_t*>(out), twd, polys);
     } else {
         bsk_permute_kernel<LOGN><<<(unsigned)sm_count * 4, 256, 0, stream>>>(
             reinterpret_cast<const double2*>(in), reinterpret_cast<double2*>(out), polys, which == 3 ? 1 : 0);
@@ -441,13 +433,13 @@ static int launch_fft_t(int which, const void* in, void* out, const double* twis
 
 // which: 0 = u64 -> thread-major Fourier, 1 = double -> canonical Fourier, 2 = canonical Fourier -> torus,
 //        3 = thread-major -> canonical, 4 = canonical -> thread-major
-int launch_fft(int which, uint32_t N, const void* in, void* out, const double* twist, const double* tw, size_t polys,
+int launch_fft(int which, uint32_t N, const void* in, void* out, const double* tw, size_t polys,
                int sm_count, cudaStream_t stream) {
     switch (N) {
-        case 512:  return launch_fft_t<9>(which, in, out, twist, tw, polys, sm_count, stream);
-        case 1024: return launch_fft_t<10>(which, in, out, twist, tw, polys, sm_count, stream);
-        case 2048: return launch_fft_t<11>(which, in, out, twist, tw, polys, sm_count, stream);
-        case 4096: return launch_fft_t<12>(which, in, out, twist, tw, polys, sm_count, stream);
+        case 512:  return launch_fft_t<9>(which, in, out, tw, polys, sm_count, stream);
+        case 1024: return launch_fft_t<10>(which, in, out, tw, polys, sm_count, stream);
+        case 2048: return launch_fft_t<11>(which, in, out, tw, polys, sm_count, stream);
+        case 4096: return launch_fft_t<12>(which, in, out, tw, polys, sm_count, stream);
         default: return set_error(TFX_ERR_UNSUPPORTED, "fft: unsupported N");
     }
 }

@@ -79,7 +79,7 @@ SYMBOLS = {
     "tfx_pbs_batch": (_I32, [_VP, _VP, _U32, _VP, _VP, _VP, _VP, _SZ, _I32, _U64]),
     "tfx_linear_conv2d": (_I32, [_VP, _VP, _U32, _U32, _U32, _U32, _VP, _U32, _U32, _U32, _U32, _U32, _VP, _U32, _U32, _U32, _VP]),
     "tfx_linear_axpby": (_I32, [_VP, _VP, _I64, _VP, _I64, _U64, _SZ, _U32, _VP]),
-    "tfx_fft_tables": (_I32, [_U32, _VP, _VP]),
+    "tfx_fft_tables": (_I32, [_U32, _VP]),
     "tfx_fft_forward": (_I32, [_VP, _U32, _VP, _SZ, _VP]),
     "tfx_fft_inverse": (_I32, [_VP, _U32, _VP, _SZ, _VP]),
     "tfx_probe_rate": (_I32, [_VP, _I32, C.POINTER(C.c_double)]),
@@ -136,10 +136,9 @@ def launch_count() -> int:
 
 
 def fft_tables(N: int):
-    twist = np.empty((N // 2, 2), dtype=np.float64)
     tw = np.empty((N // 2, 2), dtype=np.float64)
-    _check(load_library().tfx_fft_tables(N, twist.ctypes.data_as(C.c_void_p), tw.ctypes.data_as(C.c_void_p)), "tfx_fft_tables")
-    return twist, tw
+    _check(load_library().tfx_fft_tables(N, tw.ctypes.data_as(C.c_void_p)), "tfx_fft_tables")
+    return tw
 
 
 class Context:

@@ -77,7 +77,7 @@ TFX_API int tfx_keyset_set_secret(tfx_keyset* keys, int set, const uint64_t* key
 /* KSK layout u64 [big_dim][ksk_level][n+1] */
 TFX_API int tfx_keyset_get_ksk(tfx_keyset* keys, uint32_t set, uint64_t* ksk_h);
 TFX_API int tfx_keyset_set_ksk(tfx_keyset* keys, uint32_t set, const uint64_t* ksk_h);
-/* Fourier BSK in canonical layout double [n][k+1][bsk_level][k+1][N/2][2] (FFT output order) */
+/* Fourier BSK in canonical layout double [n][k+1][bsk_level][k+1][N/2][2] (transform output order, pre-scaled by 2/N) */
 TFX_API int tfx_keyset_get_bsk_fourier(tfx_keyset* keys, uint32_t set, double* bsk_h);
 TFX_API int tfx_keyset_set_bsk_fourier(tfx_keyset* keys, uint32_t set, const double* bsk_h);
 /* standard-domain BSK u64 [n][k+1][bsk_level][k+1][N]; only if generated with keep_standard_bsk */
@@ -112,8 +112,8 @@ TFX_API int tfx_linear_axpby(tfx_ctx* ctx, const uint64_t* a_d, int64_t sa, cons
                      size_t count, uint32_t words, uint64_t* out_d);
 
 /* ---- test / introspection hooks ----------------------------------------------------------------------------*/
-/* host twiddle tables exactly as uploaded to the device: twist [N/2][2], tw [N/2][2] (last entry zero) */
-TFX_API int tfx_fft_tables(uint32_t N, double* twist_h, double* tw_h);
+/* host node-twiddle table of the negacyclic transform exactly as uploaded to the device: tw [N/2][2] (last entry zero) */
+TFX_API int tfx_fft_tables(uint32_t N, double* tw_h);
 /* negacyclic FFT of P real polynomials: polys [P][N] (double) -> freq [P][N/2][2] canonical order, and back */
 TFX_API int tfx_fft_forward(tfx_ctx* ctx, uint32_t N, const double* polys_d, size_t P, double* freq_d);
 TFX_API int tfx_fft_inverse(tfx_ctx* ctx, uint32_t N, const double* freq_d, size_t P, uint64_t* torus_d);

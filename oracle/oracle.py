@@ -114,11 +114,9 @@ def keyswitch(ksk, cts, base_log, level, shift=0, body_offset=0) -> np.ndarray:
 
 
 def fft_tables(N: int):
-    M = N // 2
-    twist = np.empty((M, 2), dtype=np.float64)
-    tw = np.empty((M, 2), dtype=np.float64)
-    lib().orc_fft_tables(C.c_uint32(N), _p(twist), _p(tw))
-    return twist, tw
+    tw = np.empty((N // 2, 2), dtype=np.float64)
+    lib().orc_fft_tables(C.c_uint32(N), _p(tw))
+    return tw
 
 
 def fft_forward(poly) -> np.ndarray:

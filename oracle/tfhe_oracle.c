@@ -237,19 +237,25 @@ ORC_API void orc_keyswitch(const uint64_t* ksk, uint32_t big_dim, uint32_t n, in
 }
 
 /* ------------------------------------------------------------------------------------------------
- * 6. Negacyclic FFT.  N real coefficients <-> M = N/2 complex points.
- *    DEFINITION (the CUDA kernels regroup these radix-2 butterflies into register passes, which leaves
- *    every floating-point operation unchanged):
- *      twist[j] = exp(i*pi*j/N)                         j < M
- *      tw[s][j] = exp(i*2*pi*j/(2*half_s)), half_s = M >> (s+1),  j < half_s   (stored flat, stage s at offset M - 2*half_s)
- *      forward : z_j = (p_j + i p_{j+M}) * twist_j ; then DIF stages s = 0..log2(M)-1:
- *                  a' = a + b ; b' = (a - b) * tw[s][j]      (multiplication skipped when half_s == 1)
- *                output left in bit-reversed order (position p holds evaluation index bitrev(p)).
- *      inverse : DIT stages s = log2(M)-1..0:  b = b * conj(tw[s][j]) ; a' = a + b ; b' = a - b
- *                then r_j = z_j * conj(twist_j) ; p_j = Re(r_j)/M ; p_{j+M} = Im(r_j)/M
+ * 6. Negacyclic transform.  N real coefficients <-> M = N/2 complex values.
+ *    z_j = p_j + i p_{j+M} is evaluated at the M roots of X^M = i (all of them roots of X^N + 1), WITHOUT a
+ *    separate twist: the factor tree  X^(R h) - r  ->  prod_m (X^h - rho w_R^m),  rho = r^(1/R),  is walked with
+ *    radix-8 / radix-4 nodes ("passes").  DEFINITION of one forward node on x_0..x_{R-1} (stride 2^LO):
+ *        y_q = x_q * rho^q (q >= 1, complex multiply cmul below, rho^q from the table)
+ *        then an R-point DIF network with constant twiddles, output in bit-reversed order:
+ *          R = 8:  (q,q+4): a+b, (a-b)*w8^q   with w8^0 = 1, w8^1 = (c,c), w8^2 = i, w8^3 = (-c,c), c = sqrt(1/2)
+ *                  (q,q+2): a+b, (a-b)*{1,i} ;  (q,q+1): a+b, a-b
+ *          R = 4:  (q,q+2): a+b, (a-b)*{1,i} ;  (q,q+1): a+b, a-b
+ *        multiplication by i is (re,im) -> (-im,re); by (c,c): (c*(re-im), c*(re+im)); by (-c,c): (-(c*(re+im)), c*(re-im)).
+ *    The inverse node is the exact mirror (DIT with conjugated constants, then x_q = y_q * conj(rho^q)) and carries no
+ *    1/R: the total factor 1/M is folded into the Fourier bootstrapping key (orc_bsk_to_fourier scales by 1/M).
+ *    Pass plan (bits per pass, first pass = top index bits): log2(M)=8:{3,3,2} 9:{3,3,3} 10:{3,2,3,2} 11:{3,3,3,2}
+ *    12:{3,3,3,3}; other sizes: 3s then the remainder.  Node (pass p, high index h with S bits already split off) uses
+ *        rho = exp(i*pi*(1 + 4*bitrev_S(h)) / (R * 2^(S+1))),
+ *    rho^q = exp(i*2*pi * q*(1+4*bitrev_S(h)) / (R * 2^(S+2))) taken from cosl/sinl on the first octant + exact symmetries.
+ *    Position b of the result holds the evaluation at root number bitrev(b).
  *      cmul (a*b)      : re = fma(ar, br, -(ai*bi)) ; im = fma(ar, bi, ai*br)
  *      cmulc(a*conj b) : re = fma(ar, br,   ai*bi ) ; im = fma(ai, br, -(ar*bi))
- *    Twiddles come from cosl/sinl on the first octant + exact symmetries so that 1, i, (1+i)/sqrt2 are exact.
  * ---------------------------------------------------------------------------------------------- */
 static inline cplx cmul(cplx a, cplx b) {
     cplx r; r.re = fma(a.re, b.re, -(a.im * b.im)); r.im = fma(a.re, b.im, a.im * b.re); return r;
@@ -257,11 +263,13 @@ static inline cplx cmul(cplx a, cplx b) {
 static inline cplx cmulc(cplx a, cplx b) {
     cplx r; r.re = fma(a.re, b.re, a.im * b.im); r.im = fma(a.im, b.re, -(a.re * b.im)); return r;
 }
+static inline cplx cadd(cplx a, cplx b) { cplx r = { a.re + b.re, a.im + b.im }; return r; }
+static inline cplx csub(cplx a, cplx b) { cplx r = { a.re - b.re, a.im - b.im }; return r; }
+#define SQRT_HALF 0.70710678118654757
 
-/* exp(i*2*pi*num/den), den a power of two >= 8 or small; exact symmetries */
+/* exp(i*2*pi*num/den), den a power of two; exact symmetries */
 static cplx unit_root(uint64_t num, uint64_t den) {
     num %= den;
-    /* reduce to first octant: angle = 2*pi*num/den */
     uint64_t oct8 = (8 * num) / den;            /* 0..7 */
     uint64_t rnum = 8 * num - oct8 * den;       /* angle within octant = 2*pi*rnum/(8*den) */
     int flip = (int)(oct8 & 1);
@@ -273,13 +281,12 @@ static cplx unit_root(uint64_t num, uint64_t den) {
     if (rnum == 0 && !flip) { c = 1.0; s = 0.0; }
     else if (rnum == 0 && flip) { c = s = (double)sqrtl(0.5L); }    /* theta = pi/4 exactly */
     else { c = (double)cosl(theta); s = (double)sinl(theta); }
-    /* now (c,s) = cos/sin of an angle in [0, pi/4]; place into octant */
     double x, y;
     switch (oct8) {
-        case 0: x = c;  y = s;  break;          /* a */
-        case 1: x = s;  y = c;  break;          /* pi/2 - a' */
-        case 2: x = -s; y = c;  break;          /* pi/2 + a */
-        case 3: x = -c; y = s;  break;          /* pi - a' */
+        case 0: x = c;  y = s;  break;
+        case 1: x = s;  y = c;  break;
+        case 2: x = -s; y = c;  break;
+        case 3: x = -c; y = s;  break;
         case 4: x = -c; y = -s; break;
         case 5: x = -s; y = -c; break;
         case 6: x = s;  y = -c; break;
@@ -288,9 +295,23 @@ static cplx unit_root(uint64_t num, uint64_t den) {
     cplx r = { x, y }; return r;
 }
 
-typedef struct { uint32_t N, M, logM; cplx* twist; cplx* tw; } fft_plan;
+static uint32_t bitrev(uint32_t v, int bits) { uint32_t r = 0; for (int i = 0; i < bits; i++) r |= ((v >> i) & 1u) << (bits - 1 - i); return r; }
+
+typedef struct { uint32_t N, M, logM; int npass; int wd[8]; int lo[8]; uint32_t off[8]; cplx* tw; } fft_plan;
 
 static fft_plan* plan_cache[32];
+
+static void plan_passes(int logM, int* npass, int* wd) {
+    static const int P8[] = {3, 3, 2}, P9[] = {3, 3, 3}, P10[] = {3, 2, 3, 2}, P11[] = {3, 3, 3, 2}, P12[] = {3, 3, 3, 3};
+    const int* src = 0; int n = 0;
+    switch (logM) { case 8: src = P8; n = 3; break; case 9: src = P9; n = 3; break; case 10: src = P10; n = 4; break;
+                    case 11: src = P11; n = 4; break; case 12: src = P12; n = 4; break; default: break; }
+    if (src) { for (int i = 0; i < n; i++) wd[i] = src[i]; *npass = n; return; }
+    n = 0; int left = logM;
+    while (left >= 3) { wd[n++] = 3; left -= 3; }
+    if (left) wd[n++] = left;
+    *npass = n;
+}
 
 static fft_plan* get_plan(uint32_t N) {
     int lg = 0; while ((1u << lg) < N) lg++;
@@ -301,13 +322,18 @@ static fft_plan* get_plan(uint32_t N) {
         if (!p) {
             p = (fft_plan*)malloc(sizeof *p);
             p->N = N; p->M = N / 2; p->logM = lg - 1;
-            p->twist = (cplx*)malloc(sizeof(cplx) * p->M);
-            p->tw = (cplx*)malloc(sizeof(cplx) * p->M);
-            for (uint32_t j = 0; j < p->M; j++) p->twist[j] = unit_root(j, 2ULL * N);
-            for (uint32_t s = 0; s < p->logM; s++) {
-                uint32_t half = p->M >> (s + 1);
-                cplx* t = p->tw + (p->M - 2 * half);
-                for (uint32_t j = 0; j < half; j++) t[j] = unit_root(j, 2ULL * half);
+            plan_passes((int)p->logM, &p->npass, p->wd);
+            p->tw = (cplx*)calloc(p->M, sizeof(cplx));
+            uint32_t off = 0; int done = 0;
+            for (int q = 0; q < p->npass; q++) {
+                int wd = p->wd[q], R = 1 << wd, S = done;
+                p->lo[q] = (int)p->logM - done - wd;
+                p->off[q] = off;
+                for (uint32_t h = 0; h < (1u << S); h++)
+                    for (int e = 1; e < R; e++)
+                        p->tw[off + h * (R - 1) + (e - 1)] = unit_root((uint64_t)e * (1 + 4ULL * bitrev(h, S)), (uint64_t)R << (S + 2));
+                off += (1u << S) * (R - 1);
+                done += wd;
             }
             plan_cache[lg] = p;
         }
@@ -315,48 +341,92 @@ static fft_plan* get_plan(uint32_t N) {
     return p;
 }
 
-/* tables exported so the product's own tables can be compared in tests */
-ORC_API void orc_fft_tables(uint32_t N, double* twist /*[M][2]*/, double* tw /*[M][2], last entry unused*/) {
+/* table exported so the product's own table can be compared in tests: tw [M][2] (last entry zero) */
+ORC_API void orc_fft_tables(uint32_t N, double* tw) {
     fft_plan* p = get_plan(N);
-    memcpy(twist, p->twist, sizeof(cplx) * p->M);
-    memset(tw, 0, sizeof(cplx) * p->M);
-    memcpy(tw, p->tw, sizeof(cplx) * (p->M - 1));
+    memcpy(tw, p->tw, sizeof(cplx) * p->M);
+}
+
+static inline cplx mul_i(cplx a) { cplx r = { -a.im, a.re }; return r; }
+static inline cplx mul_mi(cplx a) { cplx r = { a.im, -a.re }; return r; }                       /* * conj(i) */
+static inline cplx mul_w8(cplx a) { cplx r = { SQRT_HALF * (a.re - a.im), SQRT_HALF * (a.re + a.im) }; return r; }
+static inline cplx mul_w83(cplx a) { cplx r = { -(SQRT_HALF * (a.re + a.im)), SQRT_HALF * (a.re - a.im) }; return r; }
+static inline cplx mul_w8c(cplx a) { cplx r = { SQRT_HALF * (a.re + a.im), SQRT_HALF * (a.im - a.re) }; return r; }   /* * conj(w8)   */
+static inline cplx mul_w83c(cplx a) { cplx r = { SQRT_HALF * (a.im - a.re), -(SQRT_HALF * (a.re + a.im)) }; return r; } /* * conj(w8^3) */
+
+static void node_forward(cplx* y, int wd, const cplx* rho) {
+    int R = 1 << wd;
+    for (int q = 1; q < R; q++) y[q] = cmul(y[q], rho[q - 1]);
+    if (wd == 3) {
+        for (int q = 0; q < 4; q++) {
+            cplx a = y[q], b = y[q + 4], d = csub(a, b);
+            y[q] = cadd(a, b);
+            y[q + 4] = (q == 0) ? d : (q == 1) ? mul_w8(d) : (q == 2) ? mul_i(d) : mul_w83(d);
+        }
+    }
+    if (wd >= 2) {
+        for (int base = 0; base < R; base += 4)
+            for (int q = 0; q < 2; q++) {
+                cplx a = y[base + q], b = y[base + q + 2], d = csub(a, b);
+                y[base + q] = cadd(a, b);
+                y[base + q + 2] = (q == 0) ? d : mul_i(d);
+            }
+    }
+    for (int base = 0; base < R; base += 2) { cplx a = y[base], b = y[base + 1]; y[base] = cadd(a, b); y[base + 1] = csub(a, b); }
+}
+
+static void node_inverse(cplx* y, int wd, const cplx* rho) {
+    int R = 1 << wd;
+    for (int base = 0; base < R; base += 2) { cplx a = y[base], b = y[base + 1]; y[base] = cadd(a, b); y[base + 1] = csub(a, b); }
+    if (wd >= 2) {
+        for (int base = 0; base < R; base += 4)
+            for (int q = 0; q < 2; q++) {
+                cplx a = y[base + q], b = y[base + q + 2];
+                if (q == 1) b = mul_mi(b);
+                y[base + q] = cadd(a, b); y[base + q + 2] = csub(a, b);
+            }
+    }
+    if (wd == 3) {
+        for (int q = 0; q < 4; q++) {
+            cplx a = y[q], b = y[q + 4];
+            b = (q == 0) ? b : (q == 1) ? mul_w8c(b) : (q == 2) ? mul_mi(b) : mul_w83c(b);
+            y[q] = cadd(a, b); y[q + 4] = csub(a, b);
+        }
+    }
+    for (int q = 1; q < R; q++) y[q] = cmulc(y[q], rho[q - 1]);
 }
 
 static void fft_forward(const fft_plan* p, const double* poly /*[N]*/, cplx* z /*[M]*/) {
     uint32_t M = p->M;
-    for (uint32_t j = 0; j < M; j++) { cplx v = { poly[j], poly[j + M] }; z[j] = cmul(v, p->twist[j]); }
-    for (uint32_t s = 0; s < p->logM; s++) {
-        uint32_t half = M >> (s + 1);
-        const cplx* t = p->tw + (M - 2 * half);
-        for (uint32_t blk = 0; blk < M; blk += 2 * half)
-            for (uint32_t j = 0; j < half; j++) {
-                cplx a = z[blk + j], b = z[blk + j + half], d;
-                z[blk + j].re = a.re + b.re; z[blk + j].im = a.im + b.im;
-                d.re = a.re - b.re; d.im = a.im - b.im;
-                z[blk + j + half] = (half == 1) ? d : cmul(d, t[j]);
+    for (uint32_t j = 0; j < M; j++) { z[j].re = poly[j]; z[j].im = poly[j + M]; }
+    cplx y[16];
+    for (int q = 0; q < p->npass; q++) {
+        int wd = p->wd[q], lo = p->lo[q], R = 1 << wd;
+        for (uint32_t h = 0; h < (M >> (lo + wd)); h++)
+            for (uint32_t l = 0; l < (1u << lo); l++) {
+                uint32_t base = (h << (lo + wd)) | l;
+                for (int e = 0; e < R; e++) y[e] = z[base + ((uint32_t)e << lo)];
+                node_forward(y, wd, p->tw + p->off[q] + h * (R - 1));
+                for (int e = 0; e < R; e++) z[base + ((uint32_t)e << lo)] = y[e];
             }
     }
 }
 
+/* inverse WITHOUT the 1/M factor: poly_j = Re z_j, poly_{j+M} = Im z_j after the mirrored passes */
 static void fft_inverse(const fft_plan* p, cplx* z /*[M], destroyed*/, double* poly /*[N]*/) {
     uint32_t M = p->M;
-    for (int s = (int)p->logM - 1; s >= 0; s--) {
-        uint32_t half = M >> (s + 1);
-        const cplx* t = p->tw + (M - 2 * half);
-        for (uint32_t blk = 0; blk < M; blk += 2 * half)
-            for (uint32_t j = 0; j < half; j++) {
-                cplx a = z[blk + j], b = z[blk + j + half];
-                if (half != 1) b = cmulc(b, t[j]);
-                z[blk + j].re = a.re + b.re; z[blk + j].im = a.im + b.im;
-                z[blk + j + half].re = a.re - b.re; z[blk + j + half].im = a.im - b.im;
+    cplx y[16];
+    for (int q = p->npass - 1; q >= 0; q--) {
+        int wd = p->wd[q], lo = p->lo[q], R = 1 << wd;
+        for (uint32_t h = 0; h < (M >> (lo + wd)); h++)
+            for (uint32_t l = 0; l < (1u << lo); l++) {
+                uint32_t base = (h << (lo + wd)) | l;
+                for (int e = 0; e < R; e++) y[e] = z[base + ((uint32_t)e << lo)];
+                node_inverse(y, wd, p->tw + p->off[q] + h * (R - 1));
+                for (int e = 0; e < R; e++) z[base + ((uint32_t)e << lo)] = y[e];
             }
     }
-    double inv = 1.0 / (double)M;
-    for (uint32_t j = 0; j < M; j++) {
-        cplx r = cmulc(z[j], p->twist[j]);
-        poly[j] = r.re * inv; poly[j + M] = r.im * inv;
-    }
+    for (uint32_t j = 0; j < M; j++) { poly[j] = z[j].re; poly[j + M] = z[j].im; }
 }
 
 /* double (integer valued up to rounding, any magnitude < 2^117) -> torus word, mod 2^64 */
@@ -376,6 +446,7 @@ ORC_API void orc_fft_inverse(uint32_t N, const double* in /*[M][2]*/, double* po
     cplx* z = (cplx*)malloc(sizeof(cplx) * p->M);
     memcpy(z, in, sizeof(cplx) * p->M);
     fft_inverse(p, z, poly);
+    for (uint32_t j = 0; j < N; j++) poly[j] *= 1.0 / (double)p->M;      /* helper returns the true inverse */
     free(z);
 }
 ORC_API void orc_double_to_torus(const double* v, uint64_t count, uint64_t* out) {
@@ -445,7 +516,9 @@ ORC_API void orc_bsk_to_fourier(const uint64_t* bsk, uint32_t n, uint32_t k, uin
         for (int64_t q = 0; q < polys; q++) {
             const uint64_t* src = bsk + (uint64_t)q * N;
             for (uint32_t t = 0; t < N; t++) tmp[t] = (double)(int64_t)src[t];
-            fft_forward(p, tmp, (cplx*)(out + (uint64_t)q * N));
+            double* dst = out + (uint64_t)q * N;
+            fft_forward(p, tmp, (cplx*)dst);
+            for (uint32_t t = 0; t < N; t++) dst[t] *= 1.0 / (double)p->M;   /* the inverse transform carries no 1/M */
         }
         free(tmp);
     }
@@ -478,7 +551,6 @@ ORC_API void orc_pbs(const double* bsk_f, uint32_t n, uint32_t k, uint32_t N, in
         uint64_t* acc = (uint64_t*)malloc(8ULL * (k + 1) * N);
         double* dpoly = (double*)malloc(8ULL * N);
         cplx* D = (cplx*)malloc(sizeof(cplx) * M);
-        cplx* part = (cplx*)malloc(sizeof(cplx) * (k + 1) * M);
         cplx* F = (cplx*)malloc(sizeof(cplx) * (k + 1) * M);
         uint64_t* diff = (uint64_t*)malloc(8ULL * N);
         int64_t dg[64];
@@ -530,7 +602,7 @@ ORC_API void orc_pbs(const double* bsk_f, uint32_t n, uint32_t k, uint32_t N, in
             uint64_t bv = acc[(uint64_t)k * N];
             if (mode == 0) o[big] = bv; else o[big] -= bv + body_const;
         }
-        free(acc); free(dpoly); free(D); free(part); free(F); free(diff);
+        free(acc); free(dpoly); free(D); free(F); free(diff);
     }
 }
 

@@ -37,14 +37,11 @@ def test_no_cpu_fallback():
 
 def test_fft_tables_equal_oracle(oracle):
     for N in (512, 1024, 2048, 4096):
-        twist, tw = binding.fft_tables(N)
-        o_twist, o_tw = oracle.fft_tables(N)
-        assert np.array_equal(twist, o_twist)
-        assert np.array_equal(tw, o_tw)
-        # exact special values the kernels rely on
-        M = N // 2
-        assert twist[0, 0] == 1.0 and twist[0, 1] == 0.0
-        assert tw[M - 4, 0] == 1.0 and tw[M - 3, 0] == 0.0 and tw[M - 3, 1] == 1.0      # half = 2 stage: 1, i
+        tw = binding.fft_tables(N)
+        assert np.array_equal(tw, oracle.fft_tables(N))
+        # first pass: one radix-8 node with rho = exp(i*pi/16): its 4th power is exactly (1+i)/sqrt(2)
+        assert tw[3, 0] == tw[3, 1] == np.float64(0.5) ** 0.5
+        assert np.allclose(tw[:-1, 0] ** 2 + tw[:-1, 1] ** 2, 1.0, atol=1e-15)
 
 
 def test_pbs_supported_matrix():
