@@ -135,13 +135,15 @@ __device__ __forceinline__ uint32_t mod_switch(uint64_t x, int log2_2N) {
     return (uint32_t)((((x >> (64 - log2_2N - 1)) + 1) >> 1) & ((1u << log2_2N) - 1));
 }
 
-// double (integer valued, |v| < 2^117) -> torus word mod 2^64
+// double (integer valued, |v| < 2^117) -> torus word mod 2^64.
+// y = v - 2^64 * rint(v / 2^64) lies in [-2^63, 2^63] (exact); round-to-nearest-even conversion.  The only value the
+// saturating conversion gets wrong is y == +2^63 (must wrap to -2^63): it comes back as INT64_MAX, which no in-range y
+// can produce (doubles near 2^63 are multiples of 1024), so it is patched with integer ops (off the FP64 pipe).
 __device__ __forceinline__ uint64_t double_to_torus(double v) {
-    double r = rint(v * 0x1p-64);
-    double y = fma(-r, 0x1p64, v);
-    if (y >= 0x1p63) y -= 0x1p64;
-    if (y < -0x1p63) y += 0x1p64;
-    return (uint64_t)__double2ll_rn(y);
+    const double r = rint(v * 0x1p-64);
+    const double y = fma(-r, 0x1p64, v);
+    const long long q = __double2ll_rn(y);
+    return (uint64_t)q + (q == 0x7fffffffffffffffLL ? 1ULL : 0ULL);
 }
 
 // ------------------------------------------------------------------------------------------------

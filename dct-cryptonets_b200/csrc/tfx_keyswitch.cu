@@ -62,7 +62,8 @@ keyswitch_kernel(KsArgs a) {
                 uint32_t r = (uint32_t)v & mask;
                 v >>= bl;
                 if (r >= half) v += 1;                                     // signed digit r - B (carry); biased: r - B + B/2
-                s_dig[wl * l + lvl][cl] = (r + half) & mask;              // d + B/2 in [0, B)
+                const uint32_t row = wl * l + lvl;                          // column groups of 4 XOR-swizzled by the row:
+                s_dig[row][cl ^ ((row & 15) << 2)] = (r + half) & mask;    // d + B/2 in [0, B); lanes walk rows -> spread banks
             }
         }
         // stage KSK rows [w0*l, w0*l + KC) x [j0, j0 + TJ)
@@ -74,7 +75,7 @@ keyswitch_kernel(KsArgs a) {
         __syncthreads();
 #pragma unroll 4
         for (int kk = 0; kk < rows_used; kk++) {
-            const uint4 dg = *reinterpret_cast<const uint4*>(&s_dig[kk][ty * 4]);
+            const uint4 dg = *reinterpret_cast<const uint4*>(&s_dig[kk][(ty * 4) ^ ((kk & 15) << 2)]);
             const ulonglong2 ka = *reinterpret_cast<const ulonglong2*>(&s_ksk[kk][tx * 2]);
             const ulonglong2 kb = *reinterpret_cast<const ulonglong2*>(&s_ksk[kk][32 + tx * 2]);
             const uint32_t d[4] = {dg.x, dg.y, dg.z, dg.w};

@@ -196,10 +196,58 @@ def tlu_apply(op: TluOp, offset: int, acc: np.ndarray) -> np.ndarray:
     return np.where(neg, -q, q)
 
 
-def evaluate_clear(circ: Circuit, q_in: np.ndarray, collect: Optional[dict] = None) -> np.ndarray:
-    """q_in int64 [B][C][H][W] -> integer outputs [B][...] (accumulator or table outputs)."""
+def tlu_apply_noisy(op: TluOp, offset: int, acc: np.ndarray, exact: bool, norm2: float, fresh: bool, nm: "NoiseModel",
+                    rng: np.random.Generator) -> np.ndarray:
+    """Like tlu_apply, but every PBS decision sees the modelled ciphertext noise: the accumulator noise
+    (weights x PBS output noise), the keyswitch + mod-switch noise at each PBS input and the output noise of every
+    extracted bit.  All quantities in units of the accumulator LSB (delta_w = 2^-(w+1) of the torus)."""
+    w, lsbs, t = op.acc_bits, op.lsbs, op.keep_bits
+    lsb = 2.0 ** -(w + 1)                                            # torus fraction of one accumulator unit
+    half = (1 << (lsbs - 1)) if (lsbs > 0 and exact) else 0
+    v_src = nm.input_var if fresh else nm.var_tlu_out
+    x = (acc + offset + half).astype(np.float64) + rng.normal(0.0, np.sqrt(norm2 * v_src) / lsb, size=acc.shape)
+    if exact:
+        for b in range(lsbs):
+            # phase of (x << (w - b)) + 1/4 turn, in turns; bit b is its top bit
+            ph = x * 2.0 ** (w - b) * lsb + 0.25 + rng.normal(0.0, np.sqrt(nm.var_bit_in), size=acc.shape)
+            bit = (np.floor(ph * 2.0) % 2.0)
+            x = x - bit * (1 << b) + rng.normal(0.0, np.sqrt(nm.var_bit_out) / lsb, size=acc.shape)
+    # table lookup on t bits + padding: index = round(phase / delta_t)
+    ph = x * lsb + rng.normal(0.0, np.sqrt(nm.var_tlu_in), size=acc.shape)
+    idx = np.floor(ph * 2.0 ** (t + 1) + 0.5).astype(np.int64) & ((1 << (t + 1)) - 1)
+    neg = idx >= (1 << t)
+    idx = idx & ((1 << t) - 1)
+    C = op.tables.shape[0]
+    ch = np.arange(C).reshape(1, C, 1, 1)
+    q = op.tables[np.broadcast_to(ch, idx.shape), idx]
+    return np.where(neg, -q, q)
+
+
+@dataclass
+class NoiseModel:
+    """variances (torus units) of the quantities a PBS decision depends on; built from the picked parameter sets"""
+    var_tlu_out: float
+    var_bit_out: float
+    var_tlu_in: float     # keyswitch + mod-switch of the table set
+    var_bit_in: float     # keyswitch + mod-switch of the bit-extraction set
+    input_var: float
+
+    @classmethod
+    def from_params(cls, tlu, bit, input_std: float) -> "NoiseModel":
+        from . import params as P
+        return cls(P.var_pbs_out(tlu), P.var_pbs_out(bit), P.var_keyswitch(tlu) + P.var_modswitch(tlu),
+                   P.var_keyswitch(bit) + P.var_modswitch(bit), input_std ** 2)
+
+
+def evaluate_clear(circ: Circuit, q_in: np.ndarray, collect: Optional[dict] = None, noise: Optional[NoiseModel] = None,
+                   rng: Optional[np.random.Generator] = None) -> np.ndarray:
+    """q_in int64 [B][C][H][W] -> integer outputs [B][...] (accumulator or table outputs).
+    noise=None: exact integer semantics.  noise=NoiseModel: Monte-Carlo of the encrypted run (fhe='simulate')."""
     vals = {circ.input_id: q_in.astype(np.int64)}
     offs = {}
+    spec = {op.dst: lk for op, lk in zip(circ.lookups(), circ.noise_spec().lookups)} if noise is not None else {}
+    if noise is not None and rng is None:
+        rng = np.random.default_rng(0)
     for op in circ.ops:
         if op.kind == "conv":
             vals[op.dst] = _int_conv(vals[op.src], op, op.raw_weight if op.raw_weight is not None else op.weight)
@@ -207,8 +255,12 @@ def evaluate_clear(circ: Circuit, q_in: np.ndarray, collect: Optional[dict] = No
         elif op.kind == "add":
             vals[op.dst] = vals[op.a] + vals[op.b]
             offs[op.dst] = op.offset
-        else:
+        elif noise is None:
             vals[op.dst] = tlu_apply(op, offs[op.src], vals[op.src])
+        else:
+            lk = spec[op.dst]
+            vals[op.dst] = tlu_apply_noisy(op, offs[op.src], vals[op.src], circ.rounding_method == "exact", lk.weight_norm2,
+                                           lk.fresh_inputs, noise, rng)
         if collect is not None:
             collect[op.dst] = vals[op.dst]
     out = vals[circ.output_id]

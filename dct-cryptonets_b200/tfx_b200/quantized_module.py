@@ -122,8 +122,14 @@ class QuantizedModule:
         if fhe not in ("disable", "simulate", "execute"):
             raise ValueError(f"fhe must be 'disable', 'simulate' or 'execute', got {fhe!r}")
         q_x = self.quantize_input(x)
-        if fhe in ("disable", "simulate"):
+        if fhe == "disable":
             q_y = C.evaluate_clear(self.fhe_circuit.circuit, q_x)
+        elif fhe == "simulate":
+            # clear integers + the modelled PBS noise of the picked parameter sets (p_error), like Concrete's simulation
+            fc = self.fhe_circuit
+            nm = C.NoiseModel.from_params(fc.params[0], fc.params[1], fc.params[0].glwe_std)
+            self._sim_calls = getattr(self, "_sim_calls", 0) + 1
+            q_y = C.evaluate_clear(fc.circuit, q_x, noise=nm, rng=np.random.default_rng(self._sim_calls))
         else:
             q_y = np.stack([self.fhe_circuit.encrypt_run_decrypt(q_x[i]) for i in range(q_x.shape[0])])
             q_y = q_y.reshape(q_x.shape[0], *self.fhe_circuit.circuit.output_shape)
