@@ -202,7 +202,13 @@ class CircuitExecutor:
         launches0 = launch_count()
         layer_t = []
         ev0 = None
-        for op in circ.ops:
+        # liveness: a layer tensor (hundreds of MB to GB) is released after its last consumer
+        last_use: Dict[int, int] = {}
+        for i, op in enumerate(circ.ops):
+            for src in ((op.src,) if op.kind != "add" else (op.a, op.b)):
+                last_use[src] = i
+        last_use[circ.output_id] = len(circ.ops)
+        for i, op in enumerate(circ.ops):
             if time_layers:
                 ev0 = torch.cuda.Event(enable_timing=True); ev0.record()
             if op.kind == "conv":
@@ -253,6 +259,8 @@ class CircuitExecutor:
             if time_layers:
                 ev1 = torch.cuda.Event(enable_timing=True); ev1.record()
                 layer_t.append((op.name, ev0, ev1))
+            for vid in [v for v in vals if last_use.get(v, -1) <= i and v != circ.output_id]:
+                del vals[vid]
         out = vals[circ.output_id].reshape(-1, words)
         if stats is not None:
             stats.launches += launch_count() - launches0
