@@ -1,6 +1,7 @@
 // tfx_api.cu — C ABI of libtfx_b200.so (declared in include/tfx.h): contexts, keysets, argument checking.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <atomic>
 #include <new>
@@ -26,6 +27,8 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 uint32_t ksk_npad(uint32_t n);
 int launch_ksk_repack(const uint64_t* src, uint64_t* dst, uint32_t rows, uint32_t n, int to_padded, cudaStream_t s);
 int launch_ksk_corr(const uint64_t* ksk_padded, uint64_t* corr, uint32_t rows, uint32_t n, int base_log, cudaStream_t s);
+int launch_ksk_bytes(const uint64_t* ksk_padded, uint8_t* kb, uint32_t rows, uint32_t n, cudaStream_t s);
+bool keyswitch_imma_ok(uint32_t big_dim, int base_log, int level);
 
 // ---- host node-twiddle table of the negacyclic transform (definition: oracle/tfhe_oracle.c section 6): roots from
 //      cosl/sinl on the first octant, the other octants by exact symmetry
@@ -98,12 +101,14 @@ using namespace tfx;
 struct tfx_ctx {
     int device; cudaStream_t stream; bool own_stream; int sm_count;
     std::vector<FftTables> tables;
+    uint8_t* scratch = nullptr; size_t scratch_bytes = 0;      // keyswitch digit matrix (tensor-core path), grown on demand
 };
 
 struct KeySet1 {
     tfx_pbs_params p;
     uint64_t* small_key_d = nullptr;   // [n]
     uint64_t* ksk_d = nullptr;         // padded [big*l][npad] + corr[npad]
+    uint8_t* ksk_bytes_d = nullptr;    // byte-split [npad*8][big*l] (tensor-core keyswitch), null if not applicable
     double* bsk_d = nullptr;           // thread-major Fourier
     uint64_t* bsk_std_d = nullptr;     // optional
     bool has_ksk = false, has_bsk = false, has_secret = false;
@@ -173,6 +178,19 @@ static int alloc_keyset(tfx_ctx* ctx, uint32_t big_dim, const tfx_pbs_params* se
     return TFX_OK;
 }
 
+// byte-split copy of the KSK for the tensor-core keyswitch (call after the padded layout + column sums are in place)
+static int build_ksk_bytes(tfx_keyset* ks, KeySet1& k1) {
+    const tfx_pbs_params& p = k1.p;
+    if (!keyswitch_imma_ok(ks->big_dim, (int)p.ksk_base_log, (int)p.ksk_level)) return TFX_OK;
+    const size_t rows = (size_t)ks->big_dim * p.ksk_level, bytes = rows * ksk_npad(p.n) * 8;
+    if (!k1.ksk_bytes_d) {
+        cudaError_t e = cudaMalloc(&k1.ksk_bytes_d, bytes);
+        if (e != cudaSuccess) return set_cuda_error(e, "cudaMalloc(ksk bytes)");
+        ks->bytes += bytes;
+    }
+    return launch_ksk_bytes(k1.ksk_d, k1.ksk_bytes_d, (uint32_t)rows, p.n, ks->ctx->stream);
+}
+
 extern "C" {
 
 const char* tfx_last_error(void) { return g_err; }
@@ -209,6 +227,7 @@ void tfx_ctx_destroy(tfx_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& t : ctx->tables) cudaFree(t.tw_d);
+    cudaFree(ctx->scratch);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -232,7 +251,7 @@ void tfx_keyset_destroy(tfx_keyset* ks) {
     cudaSetDevice(ks->ctx->device);
     cudaStreamSynchronize(ks->ctx->stream);
     cudaFree(ks->big_key_d);
-    for (auto& k1 : ks->sets) { cudaFree(k1.small_key_d); cudaFree(k1.ksk_d); cudaFree(k1.bsk_d); cudaFree(k1.bsk_std_d); }
+    for (auto& k1 : ks->sets) { cudaFree(k1.small_key_d); cudaFree(k1.ksk_d); cudaFree(k1.ksk_bytes_d); cudaFree(k1.bsk_d); cudaFree(k1.bsk_std_d); }
     delete ks;
 }
 
@@ -267,6 +286,7 @@ int tfx_keyset_generate(tfx_ctx* ctx, uint32_t big_dim, const tfx_pbs_params* se
         rc = launch_gen_ksk(seed, s, ks->big_key_d, big_dim, k1.small_key_d, p.n, p.ksk_base_log, p.ksk_level, p.lwe_std, tmp, st);
         if (!rc) rc = launch_ksk_repack(tmp, k1.ksk_d, (uint32_t)rows, p.n, 1, st);
         if (!rc) rc = launch_ksk_corr(k1.ksk_d, k1.ksk_d + rows * ksk_npad(p.n), (uint32_t)rows, p.n, p.ksk_base_log, st);
+        if (!rc) rc = build_ksk_bytes(ks, k1);
         cudaStreamSynchronize(st); cudaFree(tmp);
         if (rc) break;
         k1.has_ksk = true;
@@ -353,6 +373,7 @@ int tfx_keyset_set_ksk(tfx_keyset* ks, uint32_t set, const uint64_t* ksk_h) {
     rc = copy_sync(ks->ctx, tmp, ksk_h, words * 8, cudaMemcpyHostToDevice);
     if (!rc) rc = launch_ksk_repack(tmp, k1.ksk_d, (uint32_t)rows, k1.p.n, 1, ks->ctx->stream);
     if (!rc) rc = launch_ksk_corr(k1.ksk_d, k1.ksk_d + rows * ksk_npad(k1.p.n), (uint32_t)rows, k1.p.n, k1.p.ksk_base_log, ks->ctx->stream);
+    if (!rc) rc = build_ksk_bytes(ks, k1);
     cudaStreamSynchronize(ks->ctx->stream);
     cudaFree(tmp);
     if (!rc) k1.has_ksk = true;
@@ -433,6 +454,18 @@ int tfx_keyswitch_batch(tfx_ctx* ctx, tfx_keyset* ks, uint32_t set, const uint64
     if (!k1.has_ksk) return set_error(TFX_ERR_STATE, "keyset holds no KSK for this set");
     int rc = use_device(ctx); if (rc) return rc;
     KsLaunch p;
+    p.ksk_bytes = k1.ksk_bytes_d; p.digits = nullptr;
+    if (k1.ksk_bytes_d && !getenv("TFX_KS_IMAD")) {          // TFX_KS_IMAD=1: measurement knob, forces the integer-pipe kernel
+        const size_t need = B * (size_t)ks->big_dim * k1.p.ksk_level;
+        if (need > ctx->scratch_bytes) {
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(ctx->scratch); ctx->scratch = nullptr; ctx->scratch_bytes = 0;
+            cudaError_t e = cudaMalloc(&ctx->scratch, need);
+            if (e != cudaSuccess) return set_cuda_error(e, "cudaMalloc(keyswitch digits)");
+            ctx->scratch_bytes = need;
+        }
+        p.digits = ctx->scratch;
+    }
     p.ksk = k1.ksk_d; p.in = in_d; p.out = out_d; p.big_dim = ks->big_dim; p.n = k1.p.n; p.base_log = (int)k1.p.ksk_base_log;
     p.level = (int)k1.p.ksk_level; p.shift = shift; p.body_offset = body_offset; p.count = B; p.sm_count = ctx->sm_count;
     return launch_keyswitch(p, ctx->stream);

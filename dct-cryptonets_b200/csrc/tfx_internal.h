@@ -23,7 +23,9 @@ int launch_fft(int which, uint32_t N, const void* in, void* out, const double* t
                int sm_count, cudaStream_t stream);
 
 struct KsLaunch {
-    const uint64_t* ksk;       // device, blocked layout (see tfx_keyswitch.cu)
+    const uint64_t* ksk;       // device, padded layout + column sums (see tfx_keyswitch.cu)
+    const uint8_t* ksk_bytes;  // device, byte-split layout for the tensor-core path (or null)
+    uint8_t* digits;           // device scratch [count][big_dim*level] for the tensor-core path (or null)
     const uint64_t* in; uint64_t* out;
     uint32_t big_dim, n; int base_log, level; uint32_t shift; uint64_t body_offset; size_t count; int sm_count;
 };

@@ -91,6 +91,19 @@ def test_keyswitch_parity(gpu_ctx, oracle, p, B):
     ks.close()
 
 
+def test_keyswitch_integer_pipe_kernel_parity(gpu_ctx, oracle, monkeypatch):
+    """the IMAD keyswitch kernel (fallback when digits or accumulators do not fit the tensor-core path) against the oracle"""
+    monkeypatch.setenv("TFX_KS_IMAD", "1")
+    p = TOY[2]
+    ks = KeySet.generate(gpu_ctx, [p], 6)
+    ksk = ks.get_ksk(0)
+    rng = np.random.default_rng(9)
+    cts = rng.integers(0, 2**64, size=(130, p.big_dim + 1), dtype=np.uint64)
+    out = ks.keyswitch(0, gpu_ctx.to_device_u64(cts), shift=3, body_offset=77)
+    assert np.array_equal(gpu_ctx.to_host_u64(out), oracle.keyswitch(ksk, cts, p.ksk_base_log, p.ksk_level, shift=3, body_offset=77))
+    ks.close()
+
+
 @pytest.mark.parametrize("p", TOY, ids=IDS)
 def test_pbs_parity(gpu_ctx, oracle, p):
     seed = 11
