@@ -112,11 +112,12 @@ def cpu_sample(circ, params, sample_cts: int = 32):
         _ORACLE_KEYS = CO.OracleKeys(params, 1)
     keys = _ORACLE_KEYS
     rng = np.random.default_rng(0)
-    acc = rng.integers(0, 2**64, size=(sample_cts, tlu.big_dim + 1), dtype=np.uint64)
+    big_dim = max(tlu.big_dim, bit.big_dim)
+    acc = rng.integers(0, 2**64, size=(sample_cts, big_dim + 1), dtype=np.uint64)
     t0 = time.time()
     small = O.keyswitch(keys.ksk[1], acc, bit.ksk_base_log, bit.ksk_level, shift=12, body_offset=1 << 62)
     lut = np.full((1, bit.N), (-(1 << 50)) & (2**64 - 1), dtype=np.uint64)
-    O.pbs(keys.bsk_f[1], bit.bsk_base_log, small, lut, np.zeros(sample_cts, np.uint32), mode=1, body_const=1 << 50, out=acc)
+    O.pbs(keys.bsk_f[1], bit.bsk_base_log, small, lut, np.zeros(sample_cts, np.uint32), mode=1, body_const=1 << 50, out=acc, big_dim=big_dim)
     t_bit = (time.time() - t0) / sample_cts
     t0 = time.time()
     small = O.keyswitch(keys.ksk[0], acc, tlu.ksk_base_log, tlu.ksk_level)
@@ -266,7 +267,7 @@ def run_gpu(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {
-                "kernel": f"pbs_kernel<{'11,2' if dom == 'pbs_bit' else '12,1'}> ({dom})",
+                "kernel": f"pbs_kernel<log2N={dom_p.N.bit_length() - 1},k={dom_p.k}> ({dom})",
                 "bound": "fp64", "achieved": flops / sec / 1e12, "peak": dfma / 1e12, "unit": "TFLOP/s",
                 "frac": flops / sec / dfma, "peak_source": "DFMA rate measured live by tfx_probe_rate (MEASURED_PEAKS.json has no FP64 figure)",
                 "flops_per_pbs": P.pbs_flops(dom_p), "pbs_per_launch": units / max(1, nl), "avg_launch_ms": sec / max(1, nl) * 1e3,

@@ -147,7 +147,7 @@ static int check_params(uint32_t big_dim, const tfx_pbs_params* sets, uint32_t n
     if (!sets || nsets == 0 || nsets > 16) return set_error(TFX_ERR_ARG, "keyset: need 1..16 parameter sets");
     for (uint32_t s = 0; s < nsets; s++) {
         const tfx_pbs_params& p = sets[s];
-        if ((uint64_t)p.k * p.N != big_dim) return set_error(TFX_ERR_ARG, "keyset: k*N must equal big_dim for every set");
+        if ((uint64_t)p.k * p.N > big_dim) return set_error(TFX_ERR_ARG, "keyset: k*N must not exceed big_dim");
         if (!pbs_supported(p.N, p.k)) return set_error(TFX_ERR_UNSUPPORTED, "keyset: no PBS kernel for this (N, k)");
         if (p.n < 1 || p.n > 4096) return set_error(TFX_ERR_ARG, "keyset: n out of range");
         if (p.bsk_level < 1 || p.bsk_base_log < 1 || p.bsk_base_log * p.bsk_level > 64) return set_error(TFX_ERR_ARG, "keyset: bad BSK gadget");
@@ -485,7 +485,7 @@ int tfx_pbs_batch(tfx_ctx* ctx, tfx_keyset* ks, uint32_t set, const uint64_t* in
     rc = get_tables(ctx, k1.p.N, &tb); if (rc) return rc;
     PbsLaunch p;
     p.bsk = k1.bsk_d; p.tw = tb->tw_d; p.in = in_d; p.luts = luts_d; p.lut_index = lut_index_d; p.out = out_d;
-    p.n = k1.p.n; p.k = k1.p.k; p.N = k1.p.N; p.base_log = (int)k1.p.bsk_base_log; p.level = (int)k1.p.bsk_level;
+    p.n = k1.p.n; p.k = k1.p.k; p.N = k1.p.N; p.big_dim = ks->big_dim; p.base_log = (int)k1.p.bsk_base_log; p.level = (int)k1.p.bsk_level;
     p.mode = mode; p.body_const = body_const; p.count = B; p.sm_count = ctx->sm_count;
     return launch_pbs(p, ctx->stream);
 }

@@ -35,8 +35,8 @@ struct PbsArgs {
     const uint64_t* in;        // [B][n+1]
     const uint64_t* luts;      // [T][N]
     const uint32_t* lut_index; // [B]
-    uint64_t* out;             // [B][kN+1]
-    uint32_t n;
+    uint64_t* out;             // [B][big_dim+1], big_dim >= kN (extra mask words are zero)
+    uint32_t n, big_dim;
     int base_log, level, mode;
     uint64_t body_const;
     uint32_t count;
@@ -259,17 +259,18 @@ pbs_kernel(PbsArgs a) {
             __syncthreads();                                           // accumulator complete before the next rotation reads
         }
 
-        // sample extract coefficient 0 -> LWE under the big key
-        uint64_t* o = a.out + (size_t)ct * ((size_t)K * N + 1);
+        // sample extract coefficient 0 -> LWE under the big key (its first kN bits are this set's GLWE key)
+        uint64_t* o = a.out + (size_t)ct * ((size_t)a.big_dim + 1);
         for (int j = t; j < K * N; j += TPF) {
             int comp = j / N, tt = j - comp * N;
             const uint64_t* ar = acc + (size_t)comp * N;
             uint64_t v = (tt == 0) ? ar[0] : (uint64_t)0 - ar[N - tt];
             if (a.mode == 0) o[j] = v; else o[j] -= v;
         }
+        if (a.mode == 0) for (uint32_t j = K * N + t; j < a.big_dim; j += TPF) o[j] = 0;
         if (t == 0) {
             uint64_t bv = acc[(size_t)K * N];
-            if (a.mode == 0) o[(size_t)K * N] = bv; else o[(size_t)K * N] -= bv + a.body_const;
+            if (a.mode == 0) o[a.big_dim] = bv; else o[a.big_dim] -= bv + a.body_const;
         }
     }
 }
@@ -392,7 +393,7 @@ int launch_pbs(const PbsLaunch& p, cudaStream_t stream) {
     a.bsk = reinterpret_cast<const double2*>(p.bsk);
     a.tw = reinterpret_cast<const double2*>(p.tw);
     a.in = p.in; a.luts = p.luts; a.lut_index = p.lut_index; a.out = p.out;
-    a.n = p.n; a.base_log = p.base_log; a.level = p.level; a.mode = p.mode; a.body_const = p.body_const;
+    a.n = p.n; a.big_dim = p.big_dim; a.base_log = p.base_log; a.level = p.level; a.mode = p.mode; a.body_const = p.body_const;
     a.count = (uint32_t)p.count;
 #define TFX_PBS_CASE(LN, KK) if (p.N == (1u << LN) && p.k == KK) return launch_pbs_t<LN, KK>(a, p.sm_count, stream);
     TFX_PBS_CASE(9, 1) TFX_PBS_CASE(10, 1) TFX_PBS_CASE(11, 1) TFX_PBS_CASE(12, 1)

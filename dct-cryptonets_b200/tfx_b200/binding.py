@@ -48,6 +48,7 @@ class PbsParams:
 
     @property
     def big_dim(self) -> int:
+        """dimension of the LWE ciphertexts this set's sample extraction produces (k*N); a keyset's big key may be longer"""
         return self.k * self.N
 
 
@@ -234,7 +235,7 @@ class KeySet:
 
     def __init__(self, ctx: Context, params: Sequence[PbsParams], handle):
         self.ctx, self.params, self.h = ctx, list(params), handle
-        self.big_dim = params[0].big_dim
+        self.big_dim = max(p.big_dim for p in params)           # the big LWE key; every set's GLWE key is a prefix of it
 
     # -- construction -------------------------------------------------------------------------------
     @staticmethod
@@ -245,14 +246,14 @@ class KeySet:
     @classmethod
     def generate(cls, ctx: Context, params: Sequence[PbsParams], seed, keep_standard_bsk: bool = False) -> "KeySet":
         h = C.c_void_p()
-        _check(ctx.lib.tfx_keyset_generate(ctx.h, params[0].big_dim, cls._carr(params), len(params), _seed_buf(seed),
+        _check(ctx.lib.tfx_keyset_generate(ctx.h, max(p.big_dim for p in params), cls._carr(params), len(params), _seed_buf(seed),
                                            int(keep_standard_bsk), C.byref(h)), "tfx_keyset_generate")
         return cls(ctx, params, h)
 
     @classmethod
     def empty(cls, ctx: Context, params: Sequence[PbsParams]) -> "KeySet":
         h = C.c_void_p()
-        _check(ctx.lib.tfx_keyset_create_empty(ctx.h, params[0].big_dim, cls._carr(params), len(params), C.byref(h)),
+        _check(ctx.lib.tfx_keyset_create_empty(ctx.h, max(p.big_dim for p in params), cls._carr(params), len(params), C.byref(h)),
                "tfx_keyset_create_empty")
         return cls(ctx, params, h)
 

@@ -235,8 +235,9 @@ class NoiseModel:
     @classmethod
     def from_params(cls, tlu, bit, input_std: float) -> "NoiseModel":
         from . import params as P
-        return cls(P.var_pbs_out(tlu), P.var_pbs_out(bit), P.var_keyswitch(tlu) + P.var_modswitch(tlu),
-                   P.var_keyswitch(bit) + P.var_modswitch(bit), input_std ** 2)
+        big = max(tlu.k * tlu.N, bit.k * bit.N)
+        return cls(P.var_pbs_out(tlu), P.var_pbs_out(bit), P.var_keyswitch(tlu, big) + P.var_modswitch(tlu),
+                   P.var_keyswitch(bit, big) + P.var_modswitch(bit), input_std ** 2)
 
 
 def evaluate_clear(circ: Circuit, q_in: np.ndarray, collect: Optional[dict] = None, noise: Optional[NoiseModel] = None,

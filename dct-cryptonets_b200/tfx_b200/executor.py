@@ -97,7 +97,7 @@ class CircuitExecutor:
         self.ctx = ctx if ctx is not None else Context(torch.cuda.current_device())
         self.rank, self.world = rank, world_size
         self.pg = process_group
-        self.big_dim = params[0].big_dim
+        self.big_dim = max(p.big_dim for p in params)
         self.words = self.big_dim + 1
         self.input_std = input_std if input_std is not None else params[0].glwe_std
         self.keys: Optional[KeySet] = None

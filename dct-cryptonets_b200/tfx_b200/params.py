@@ -19,6 +19,7 @@ from typing import Iterable, List, Optional, Sequence, Tuple
 from .binding import PbsParams
 
 SUPPORTED_KN = {1: (512, 1024, 2048, 4096), 2: (512, 1024, 2048)}
+DEFAULT_BIG_DIM = 4096      # big LWE key of the circuits compiled here (the table set is (k=1, N=4096))
 
 
 def z_score(p_error: float) -> float:
@@ -63,9 +64,10 @@ def var_pbs_out(p: PbsParams) -> float:
     return p.n * per
 
 
-def var_keyswitch(p: PbsParams) -> float:
+def var_keyswitch(p: PbsParams, big_dim: Optional[int] = None) -> float:
+    """keyswitch of a big-key ciphertext (all big_dim mask words) to this set's small key"""
     B2 = 2.0 ** (2 * p.ksk_base_log)
-    kN = p.k * p.N
+    kN = big_dim if big_dim is not None else p.k * p.N
     return kN * (p.ksk_level * (B2 + 2.0) / 12.0 * p.lwe_std ** 2 + 1.0 / (24.0 * 2.0 ** (2 * p.ksk_base_log * p.ksk_level)))
 
 
@@ -83,12 +85,13 @@ def bsk_bytes(p: PbsParams) -> int:
     return p.n * p.bsk_level * (p.k + 1) ** 2 * (p.N // 2) * 16
 
 
-def ks_macs(p: PbsParams) -> int:
-    return p.k * p.N * p.ksk_level * (p.n + 1)
+def ks_macs(p: PbsParams, big_dim: Optional[int] = None) -> int:
+    kN = big_dim if big_dim is not None else p.k * p.N
+    return kN * p.ksk_level * (p.n + 1)
 
 
-def ksk_bytes(p: PbsParams) -> int:
-    return 8 * ks_macs(p)
+def ksk_bytes(p: PbsParams, big_dim: Optional[int] = None) -> int:
+    return 8 * ks_macs(p, big_dim)
 
 
 @dataclass
@@ -111,8 +114,9 @@ class CircuitNoiseSpec:
 def _check(spec: CircuitNoiseSpec, tlu: PbsParams, bit: PbsParams, z: float) -> Tuple[bool, float]:
     """True iff every PBS input in the circuit keeps failure probability <= p_error.  Also returns the worst margin."""
     vA, vB = var_pbs_out(tlu), var_pbs_out(bit)
-    v_in_tlu = var_keyswitch(tlu) + var_modswitch(tlu)
-    v_in_bit = var_keyswitch(bit) + var_modswitch(bit)
+    big = max(tlu.k * tlu.N, bit.k * bit.N)
+    v_in_tlu = var_keyswitch(tlu, big) + var_modswitch(tlu)
+    v_in_bit = var_keyswitch(bit, big) + var_modswitch(bit)
     worst = float("inf")
     for lk in spec.lookups:
         v_src = spec.input_std ** 2 if lk.fresh_inputs else vA
@@ -139,7 +143,8 @@ def _cost(spec: CircuitNoiseSpec, tlu: PbsParams, bit: PbsParams) -> float:
         cnt = max(1, lk.count)
         nb = max(0, lk.acc_bits - lk.keep_bits)
         # 2 integer ops per keyswitch MAC weigh roughly like 1/4 flop of PBS time on this machine; keep KS visible but small
-        c += cnt * (pbs_flops(tlu) + 0.5 * ks_macs(tlu)) + cnt * nb * (pbs_flops(bit) + 0.5 * ks_macs(bit))
+        big = max(tlu.k * tlu.N, bit.k * bit.N)
+        c += cnt * (pbs_flops(tlu) + 0.5 * ks_macs(tlu, big)) + cnt * nb * (pbs_flops(bit) + 0.5 * ks_macs(bit, big))
     return c
 
 
@@ -190,7 +195,9 @@ def pick_parameters(spec: CircuitNoiseSpec, big_dim: int = 4096, n_step: int = 1
     has_bits = any(lk.acc_bits > lk.keep_bits for lk in lookups)
     best = None
     tlu_shapes = [(1, big_dim)] if big_dim in SUPPORTED_KN[1] else []
-    bit_shapes = [(k, big_dim // k) for k in (1, 2) if big_dim % k == 0 and (big_dim // k) in SUPPORTED_KN[k]]
+    # the bit-extraction set may use a GLWE key that is a prefix of the big key (k*N <= big_dim): its sample-extracted
+    # ciphertext, zero-padded, is a ciphertext under the big key; security and noise follow its own dimension k*N
+    bit_shapes = [(k, N) for k in (1, 2) for N in SUPPORTED_KN[k] if k * N <= big_dim and k * N >= 2048]
     for (kA, NA) in tlu_shapes:
         for nA in range(400, 1300, n_step):
             budget_tlu = (2.0 ** -(t_max + 2) / z) ** 2
@@ -238,7 +245,7 @@ def pick_parameters(spec: CircuitNoiseSpec, big_dim: int = 4096, n_step: int = 1
                         # (v_acc + b*vB) * 2^(2(w-b)) must stay inside half of the sign-decision budget, and the final
                         # table lookup must still see v_acc + lsbs*vB + v_ks + v_ms inside its own budget
                         needB = float("inf")
-                        v_in_tlu = var_keyswitch(tlu) + var_modswitch(tlu)
+                        v_in_tlu = var_keyswitch(tlu, big_dim) + var_modswitch(tlu)
                         for lk in lookups:
                             nbits = lk.acc_bits - lk.keep_bits
                             if nbits <= 0:
@@ -265,13 +272,13 @@ def pick_parameters(spec: CircuitNoiseSpec, big_dim: int = 4096, n_step: int = 1
     cost, tlu, bit, margin = best
     info = {
         "z": z, "p_error": spec.p_error, "cost_model": cost, "worst_margin": margin,
-        "tlu": {"sigma_pbs_out_log2": 0.5 * math.log2(var_pbs_out(tlu)), "sigma_ks_log2": 0.5 * math.log2(var_keyswitch(tlu)),
+        "tlu": {"sigma_pbs_out_log2": 0.5 * math.log2(var_pbs_out(tlu)), "sigma_ks_log2": 0.5 * math.log2(var_keyswitch(tlu, big_dim)),
                 "sigma_ms_log2": 0.5 * math.log2(var_modswitch(tlu)),
                 "sigma_fft_log2": 0.5 * math.log2(tlu.n * var_fft_extprod(tlu.k, tlu.N, tlu.bsk_base_log, tlu.bsk_level)),
-                "flops": pbs_flops(tlu), "bsk_bytes": bsk_bytes(tlu), "ks_macs": ks_macs(tlu)},
-        "bit": {"sigma_pbs_out_log2": 0.5 * math.log2(var_pbs_out(bit)), "sigma_ks_log2": 0.5 * math.log2(var_keyswitch(bit)),
+                "flops": pbs_flops(tlu), "bsk_bytes": bsk_bytes(tlu), "ks_macs": ks_macs(tlu, big_dim)},
+        "bit": {"sigma_pbs_out_log2": 0.5 * math.log2(var_pbs_out(bit)), "sigma_ks_log2": 0.5 * math.log2(var_keyswitch(bit, big_dim)),
                 "sigma_ms_log2": 0.5 * math.log2(var_modswitch(bit)),
                 "sigma_fft_log2": 0.5 * math.log2(bit.n * var_fft_extprod(bit.k, bit.N, bit.bsk_base_log, bit.bsk_level)),
-                "flops": pbs_flops(bit), "bsk_bytes": bsk_bytes(bit), "ks_macs": ks_macs(bit)},
+                "flops": pbs_flops(bit), "bsk_bytes": bsk_bytes(bit), "ks_macs": ks_macs(bit, big_dim)},
     }
     return tlu, bit, info

@@ -39,9 +39,11 @@ extern "C" {
 typedef struct tfx_ctx tfx_ctx;
 typedef struct tfx_keyset tfx_keyset;
 
-/* One PBS flavour: small LWE key of dimension n, GLWE (k, N) with k*N == big_dim of the keyset,
- * bootstrapping-key gadget (2^bsk_base_log, bsk_level), keyswitch-key gadget (2^ksk_base_log, ksk_level).
- * Noise standard deviations are fractions of the torus. */
+/* One PBS flavour: small LWE key of dimension n, GLWE (k, N) with k*N <= big_dim of the keyset (its GLWE key is the
+ * first k*N bits of the big LWE key, so a sample-extracted ciphertext, zero-padded to big_dim, is a ciphertext under
+ * the big key), bootstrapping-key gadget (2^bsk_base_log, bsk_level), keyswitch-key gadget (2^ksk_base_log,
+ * ksk_level; the KSK always maps all big_dim mask words to the small key).  Noise standard deviations are fractions
+ * of the torus. */
 typedef struct tfx_pbs_params {
     uint32_t n, k, N;
     uint32_t bsk_base_log, bsk_level;
@@ -97,7 +99,7 @@ TFX_API int tfx_lwe_phase(tfx_ctx* ctx, tfx_keyset* keys, int key_sel, const uin
  * scaled by 2^shift and body_offset is added to the body (rounding chain; 0/0 for a plain keyswitch). */
 TFX_API int tfx_keyswitch_batch(tfx_ctx* ctx, tfx_keyset* keys, uint32_t set, const uint64_t* in_d, uint64_t* out_d, size_t B,
                         uint32_t shift, uint64_t body_offset);
-/* programmable bootstrap: in [B][n+1], luts [T][N], lut_index [B] -> out [B][big_dim+1].
+/* programmable bootstrap: in [B][n+1], luts [T][N], lut_index [B] -> out [B][big_dim+1] (mask words k*N..big_dim-1 are zero).
  * mode 0: out = PBS(in);  mode 1: out -= PBS(in) + (0,..,0,body_const)  (bit-extraction step fused). */
 TFX_API int tfx_pbs_batch(tfx_ctx* ctx, tfx_keyset* keys, uint32_t set, const uint64_t* in_d, const uint64_t* luts_d,
                   const uint32_t* lut_index_d, uint64_t* out_d, size_t B, int mode, uint64_t body_const);

@@ -22,7 +22,8 @@ class OracleKeys:
 
     def __init__(self, params, seed, with_bsk_sets=None):
         self.params = list(params)
-        self.big = O.gen_binary_key(seed, O.ST_BIGKEY, 0, params[0].k * params[0].N)
+        self.big_dim = max(p.k * p.N for p in params)
+        self.big = O.gen_binary_key(seed, O.ST_BIGKEY, 0, self.big_dim)
         self.small, self.ksk, self.bsk_f = [], [], []
         for s, p in enumerate(params):
             small = O.gen_binary_key(seed, O.ST_SMALLKEY, s, p.n)
@@ -108,7 +109,8 @@ def run_circuit(circ, keys: OracleKeys, in_cts: np.ndarray, collect: Optional[Di
                 t1 = time.time()
                 c = 1 << (62 - w + b)
                 lut = np.full((1, bit_p.N), (-c) & MASK64, dtype=np.uint64)
-                O.pbs(keys.bsk_f[1], bit_p.bsk_base_log, small, lut, np.zeros(acc.shape[0], np.uint32), mode=1, body_const=c, out=acc)
+                O.pbs(keys.bsk_f[1], bit_p.bsk_base_log, small, lut, np.zeros(acc.shape[0], np.uint32), mode=1, body_const=c, out=acc,
+                      big_dim=words - 1)
                 t2 = time.time()
                 t_ks += t1 - t0; t_pbs += t2 - t1
             t0 = time.time()
@@ -116,7 +118,7 @@ def run_circuit(circ, keys: OracleKeys, in_cts: np.ndarray, collect: Optional[Di
             t1 = time.time()
             luts = np.stack([lut_poly(op.tables[c], op.keep_bits, tlu_p.N, op.out_width) for c in range(C)])
             idx = np.repeat(np.arange(C, dtype=np.uint32), H * W)
-            out = O.pbs(keys.bsk_f[0], tlu_p.bsk_base_log, small, luts, idx)
+            out = O.pbs(keys.bsk_f[0], tlu_p.bsk_base_log, small, luts, idx, big_dim=words - 1)
             t2 = time.time()
             t_ks += t1 - t0; t_pbs += t2 - t1
             vals[op.dst] = out.reshape(C, H, W, words)

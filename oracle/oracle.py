@@ -152,7 +152,7 @@ def poly_mul_negacyclic(a, b) -> np.ndarray:
 
 def gen_bsk(small_key, big_key, k, N, base_log, level, std, seed, set_id=0) -> np.ndarray:
     small_key = np.ascontiguousarray(small_key, dtype=np.uint64)
-    big_key = np.ascontiguousarray(big_key, dtype=np.uint64)
+    big_key = np.ascontiguousarray(big_key, dtype=np.uint64)[: k * N]      # the GLWE key is the first k*N bits of the big key
     assert big_key.size == k * N
     n = small_key.size
     out = np.empty((n, k + 1, level, k + 1, N), dtype=np.uint64)
@@ -169,18 +169,20 @@ def bsk_to_fourier(bsk) -> np.ndarray:
     return out
 
 
-def pbs(bsk_f, base_log, cts, luts, lut_index, mode=0, body_const=0, out=None) -> np.ndarray:
+def pbs(bsk_f, base_log, cts, luts, lut_index, mode=0, body_const=0, out=None, big_dim=None) -> np.ndarray:
     n, k1, level, _, M, _ = bsk_f.shape
     k, N = k1 - 1, 2 * M
+    big = k * N if big_dim is None else int(big_dim)
+    assert big >= k * N
     cts = np.ascontiguousarray(cts, dtype=np.uint64).reshape(-1, n + 1)
     luts = np.ascontiguousarray(luts, dtype=np.uint64).reshape(-1, N)
     lut_index = np.ascontiguousarray(lut_index, dtype=np.uint32).ravel()
     assert lut_index.size == cts.shape[0] and (lut_index.max(initial=0) < luts.shape[0])
     if out is None:
         assert mode == 0
-        out = np.empty((cts.shape[0], k * N + 1), dtype=np.uint64)
-    assert out.flags.c_contiguous and out.shape == (cts.shape[0], k * N + 1)
-    lib().orc_pbs(_p(bsk_f), C.c_uint32(n), C.c_uint32(k), C.c_uint32(N), C.c_int(base_log), C.c_int(level),
+        out = np.empty((cts.shape[0], big + 1), dtype=np.uint64)
+    assert out.flags.c_contiguous and out.shape == (cts.shape[0], big + 1)
+    lib().orc_pbs(_p(bsk_f), C.c_uint32(n), C.c_uint32(k), C.c_uint32(N), C.c_uint32(big), C.c_int(base_log), C.c_int(level),
                   _p(cts), _p(luts), _p(lut_index), C.c_uint64(cts.shape[0]), C.c_int(mode),
                   C.c_uint64(body_const & (2**64 - 1)), _p(out))
     return out

@@ -527,7 +527,8 @@ ORC_API void orc_bsk_to_fourier(const uint64_t* bsk, uint32_t n, uint32_t k, uin
 /* ------------------------------------------------------------------------------------------------
  * 8. Programmable bootstrap.
  *    in  : u64 [B][n+1] under the small key; luts u64 [T][N]; lut_index u32 [B]
- *    out : u64 [B][kN+1] under the big key.
+ *    out : u64 [B][big_dim+1] under the big key, big_dim >= kN: the GLWE key is the first kN bits of the big key, the
+ *          remaining mask words are zero (mode 0) / untouched (mode 1).
  *    mode 0: out = result ; mode 1: out -= (result + (0,..,0,body_const))   (rounding chain, A.7 step 4)
  *    MAC order (fixed): F_c = one fma chain starting from 0 over (r ascending, lvl ascending).
  * ---------------------------------------------------------------------------------------------- */
@@ -541,11 +542,11 @@ static inline uint64_t rot_coeff(const uint64_t* p, uint32_t N, uint32_t j, uint
     return idx < N ? p[idx] : (uint64_t)0 - p[idx - N];
 }
 
-ORC_API void orc_pbs(const double* bsk_f, uint32_t n, uint32_t k, uint32_t N, int base_log, int level,
+ORC_API void orc_pbs(const double* bsk_f, uint32_t n, uint32_t k, uint32_t N, uint32_t big, int base_log, int level,
                      const uint64_t* in, const uint64_t* luts, const uint32_t* lut_index, uint64_t count,
                      int mode, uint64_t body_const, uint64_t* out) {
     fft_plan* p = get_plan(N);
-    uint32_t M = N / 2, log2_2N = p->logM + 2, big = k * N;
+    uint32_t M = N / 2, log2_2N = p->logM + 2;
 #pragma omp parallel
     {
         uint64_t* acc = (uint64_t*)malloc(8ULL * (k + 1) * N);
@@ -599,6 +600,7 @@ ORC_API void orc_pbs(const double* bsk_f, uint32_t n, uint32_t k, uint32_t N, in
                     if (mode == 0) o[r * N + t] = v; else o[r * N + t] -= v;
                 }
             }
+            if (mode == 0) for (uint32_t t = k * N; t < big; t++) o[t] = 0;
             uint64_t bv = acc[(uint64_t)k * N];
             if (mode == 0) o[big] = bv; else o[big] -= bv + body_const;
         }

@@ -112,7 +112,7 @@ def test_parameter_picker_meets_noise_constraints(tiny):
     m, calib, circ = tiny
     spec = circ.noise_spec()
     tlu, bit, info = P.pick_parameters(spec)
-    assert tlu.k * tlu.N == bit.k * bit.N == 4096
+    assert tlu.k * tlu.N == 4096 and bit.k * bit.N in (2048, 4096)       # the bit set may use a prefix of the big key
     ok, margin = P._check(spec, tlu, bit, P.z_score(spec.p_error))
     assert ok and margin >= 1.0 and abs(info["z"] - 2.5758) < 1e-3
     # a smaller p_error must never yield cheaper parameters; an unreachable one must fail loudly

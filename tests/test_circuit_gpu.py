@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 # insecure toy sets with negligible noise: outputs must equal the clear evaluation exactly
 TOY_TLU = PbsParams(n=96, k=1, N=2048, bsk_base_log=12, bsk_level=3, ksk_base_log=4, ksk_level=6, lwe_std=2.0**-40, glwe_std=2.0**-55)
-TOY_BIT = PbsParams(n=80, k=2, N=1024, bsk_base_log=12, bsk_level=3, ksk_base_log=4, ksk_level=6, lwe_std=2.0**-40, glwe_std=2.0**-55)
+TOY_BIT = PbsParams(n=80, k=2, N=512, bsk_base_log=12, bsk_level=3, ksk_base_log=4, ksk_level=6, lwe_std=2.0**-40, glwe_std=2.0**-55)
 
 
 class TinyNet(nn.Module):

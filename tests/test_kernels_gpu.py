@@ -225,3 +225,44 @@ def test_eval_only_keyset_roundtrip(gpu_ctx, oracle):
     with pytest.raises(Exception):
         ks.phase(cts)
     ks.close(); ev.close()
+
+
+def test_prefix_glwe_key_sets(gpu_ctx, oracle):
+    """a PBS set whose GLWE key is a prefix of the big key (k*N < big_dim): keys, PBS output rows (zero-padded to the big
+    dimension, both modes) equal the oracle's, and the result decrypts under the big key"""
+    pa = PbsParams(n=40, k=1, N=2048, bsk_base_log=12, bsk_level=2, ksk_base_log=4, ksk_level=5, lwe_std=2.0**-30, glwe_std=2.0**-50)
+    pb = PbsParams(n=32, k=2, N=512, bsk_base_log=10, bsk_level=2, ksk_base_log=4, ksk_level=5, lwe_std=2.0**-30, glwe_std=2.0**-45)
+    seed = 17
+    ks = KeySet.generate(gpu_ctx, [pa, pb], seed, keep_standard_bsk=True)
+    assert ks.big_dim == 2048
+    big = oracle.gen_binary_key(seed, oracle.ST_BIGKEY, 0, 2048)
+    small_b = oracle.gen_binary_key(seed, oracle.ST_SMALLKEY, 1, pb.n)
+    assert np.array_equal(ks.get_secret(-1), big) and np.array_equal(ks.get_secret(1), small_b)
+    ksk_b = oracle.gen_ksk(big, small_b, pb.ksk_base_log, pb.ksk_level, pb.lwe_std, seed, 1)
+    assert np.array_equal(ks.get_ksk(1), ksk_b)                                   # keyswitch key covers all 2048 mask words
+    bsk_b = oracle.gen_bsk(small_b, big, pb.k, pb.N, pb.bsk_base_log, pb.bsk_level, pb.glwe_std, seed, 1)
+    assert np.array_equal(ks.get_bsk_standard(1), bsk_b)
+    bsk_f = oracle.bsk_to_fourier(bsk_b)
+    rng = np.random.default_rng(10)
+    B = 7
+    cts = rng.integers(0, 2**64, size=(B, pb.n + 1), dtype=np.uint64)
+    luts = rng.integers(0, 2**64, size=(2, pb.N), dtype=np.uint64)
+    idx = rng.integers(0, 2, size=B).astype(np.uint32)
+    d_idx = torch.from_numpy(idx.astype(np.int32)).to(gpu_ctx.device)
+    out = gpu_ctx.to_host_u64(ks.pbs(1, gpu_ctx.to_device_u64(cts), gpu_ctx.to_device_u64(luts), d_idx))
+    ref = oracle.pbs(bsk_f, pb.bsk_base_log, cts, luts, idx, big_dim=2048)
+    assert out.shape == (B, 2049) and np.array_equal(out, ref) and not out[:, 1024:2048].any()
+    base = rng.integers(0, 2**64, size=(B, 2049), dtype=np.uint64)
+    d_base = gpu_ctx.to_device_u64(base)
+    ks.pbs(1, gpu_ctx.to_device_u64(cts), gpu_ctx.to_device_u64(luts), d_idx, mode=1, body_const=5, out=d_base)
+    ref2 = oracle.pbs(bsk_f, pb.bsk_base_log, cts, luts, idx, mode=1, body_const=5, out=base.copy(), big_dim=2048)
+    assert np.array_equal(gpu_ctx.to_host_u64(d_base), ref2)
+    # functional: encrypt under the big key, keyswitch to set 1, sign-PBS, decrypt under the big key
+    msgs = np.array([0, 1] * 8, dtype=np.uint64)
+    enc = ks.encrypt(gpu_ctx.to_device_u64((msgs << np.uint64(63)) + np.uint64(1 << 62)), 2.0**-45, 3)
+    c = 1 << 60
+    sign_lut = gpu_ctx.to_device_u64(np.full((1, pb.N), (-c) % 2**64, dtype=np.uint64))
+    res = ks.pbs(1, ks.keyswitch(1, enc), sign_lut, torch.zeros(16, dtype=torch.int32, device=gpu_ctx.device))
+    ph = gpu_ctx.to_host_u64(ks.phase(res)).view(np.int64)
+    assert np.array_equal(ph > 0, msgs.astype(bool)) and np.all(np.abs(np.abs(ph) - c) < 2**50)
+    ks.close()

@@ -27,7 +27,7 @@ def _worker(rank, world, port, ret):
         calib = torch.randn(32, 3, 4, 4)
         circ = C.build_circuit(net, calib, 5, 6, 0.01)
         tlu = PbsParams(n=96, k=1, N=2048, bsk_base_log=12, bsk_level=3, ksk_base_log=4, ksk_level=6, lwe_std=2.0**-40, glwe_std=2.0**-55)
-        bit = PbsParams(n=80, k=2, N=1024, bsk_base_log=12, bsk_level=3, ksk_base_log=4, ksk_level=6, lwe_std=2.0**-40, glwe_std=2.0**-55)
+        bit = PbsParams(n=80, k=2, N=512, bsk_base_log=12, bsk_level=3, ksk_base_log=4, ksk_level=6, lwe_std=2.0**-40, glwe_std=2.0**-55)
         ctx = Context(rank)
         q = C.quantize_input(circ, calib[:1].numpy())[0]
         single = CircuitExecutor(circ, (tlu, bit), ctx=ctx, input_std=2.0**-50)

@@ -21,8 +21,13 @@ from tfx_b200.binding import Context, KeySet, PbsParams   # noqa: E402
 DEFAULT_SETS = {
     "tlu": PbsParams(n=752, k=1, N=4096, bsk_base_log=16, bsk_level=2, ksk_base_log=2, ksk_level=7,
                      lwe_std=P.min_noise_std(752), glwe_std=P.min_noise_std(4096)),
-    "bit": PbsParams(n=524, k=2, N=2048, bsk_base_log=24, bsk_level=1, ksk_base_log=2, ksk_level=5,
-                     lwe_std=P.min_noise_std(524), glwe_std=P.min_noise_std(4096)),
+    # bit-extraction set: its GLWE key is the first k*N = 2048 bits of the 4096-bit big key
+    "bit": PbsParams(n=516, k=2, N=1024, bsk_base_log=23, bsk_level=1, ksk_base_log=2, ksk_level=5,
+                     lwe_std=P.min_noise_std(516), glwe_std=P.min_noise_std(2048)),
+    "bit_k1": PbsParams(n=516, k=1, N=2048, bsk_base_log=23, bsk_level=1, ksk_base_log=2, ksk_level=5,
+                        lwe_std=P.min_noise_std(516), glwe_std=P.min_noise_std(2048)),
+    "bit_full": PbsParams(n=524, k=2, N=2048, bsk_base_log=24, bsk_level=1, ksk_base_log=2, ksk_level=5,
+                          lwe_std=P.min_noise_std(524), glwe_std=P.min_noise_std(4096)),
 }
 
 
@@ -62,11 +67,11 @@ def main():
     for B in [int(b) for b in args.batches.split(",")]:
         for sid, (name, p) in enumerate(zip(names, sets)):
             g = torch.Generator(device="cuda"); g.manual_seed(B)
-            big = torch.randint(-2**62, 2**62, (B, p.big_dim + 1), dtype=torch.int64, device=ctx.device, generator=g)
+            big = torch.randint(-2**62, 2**62, (B, keys.big_dim + 1), dtype=torch.int64, device=ctx.device, generator=g)
             small = torch.randint(-2**62, 2**62, (B, p.n + 1), dtype=torch.int64, device=ctx.device, generator=g)
             luts = torch.randint(-2**62, 2**62, (4, p.N), dtype=torch.int64, device=ctx.device, generator=g)
             idx = torch.zeros(B, dtype=torch.int32, device=ctx.device)
-            out = ctx.empty_u64(B, p.big_dim + 1)
+            out = ctx.empty_u64(B, keys.big_dim + 1)
             ks_out = ctx.empty_u64(B, p.n + 1)
             t_pbs = time_fn(lambda: keys.pbs(sid, small, luts, idx, out=out), args.warmup, args.iters, flush)
             row = {"set": name, "B": B, "pbs_s": t_pbs, "pbs_per_s": B / t_pbs,
@@ -74,8 +79,8 @@ def main():
                    "bsk_GBps_algorithmic": P.bsk_bytes(p) / t_pbs / 1e9}
             if not args.no_ks:
                 t_ks = time_fn(lambda: keys.keyswitch(sid, big, out=ks_out), args.warmup, args.iters, flush)
-                row.update({"ks_s": t_ks, "ks_per_s": B / t_ks, "ks_tmacs": B * P.ks_macs(p) / t_ks / 1e12,
-                            "ks_frac_imac": B * P.ks_macs(p) / t_ks / imac})
+                macs = P.ks_macs(p, keys.big_dim)
+                row.update({"ks_s": t_ks, "ks_per_s": B / t_ks, "ks_tmacs": B * macs / t_ks / 1e12, "ks_frac_imac": B * macs / t_ks / imac})
             rows.append(row)
             print(json.dumps(row), flush=True)
     if args.json:
