@@ -102,6 +102,7 @@ struct tfx_ctx {
     int device; cudaStream_t stream; bool own_stream; int sm_count;
     std::vector<FftTables> tables;
     uint8_t* scratch = nullptr; size_t scratch_bytes = 0;      // keyswitch digit matrix (tensor-core path), grown on demand
+    uint32_t* work_counter = nullptr;                          // dynamic ciphertext hand-out of the PBS kernel
 };
 
 struct KeySet1 {
@@ -228,6 +229,7 @@ void tfx_ctx_destroy(tfx_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto& t : ctx->tables) cudaFree(t.tw_d);
     cudaFree(ctx->scratch);
+    cudaFree(ctx->work_counter);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -483,7 +485,12 @@ int tfx_pbs_batch(tfx_ctx* ctx, tfx_keyset* ks, uint32_t set, const uint64_t* in
     int rc = use_device(ctx); if (rc) return rc;
     FftTables* tb = nullptr;
     rc = get_tables(ctx, k1.p.N, &tb); if (rc) return rc;
+    if (!ctx->work_counter) {
+        cudaError_t e = cudaMalloc(&ctx->work_counter, 64);
+        if (e != cudaSuccess) return set_cuda_error(e, "cudaMalloc(pbs work counter)");
+    }
     PbsLaunch p;
+    p.work_counter = ctx->work_counter;
     p.bsk = k1.bsk_d; p.tw = tb->tw_d; p.in = in_d; p.luts = luts_d; p.lut_index = lut_index_d; p.out = out_d;
     p.n = k1.p.n; p.k = k1.p.k; p.N = k1.p.N; p.big_dim = ks->big_dim; p.base_log = (int)k1.p.bsk_base_log; p.level = (int)k1.p.bsk_level;
     p.mode = mode; p.body_const = body_const; p.count = B; p.sm_count = ctx->sm_count;

@@ -16,6 +16,7 @@ struct PbsLaunch {
     const double* bsk; const double* tw;
     const uint64_t* in; const uint64_t* luts; const uint32_t* lut_index; uint64_t* out;
     uint32_t n, k, N, big_dim; int base_log, level, mode; uint64_t body_const; size_t count; int sm_count;
+    uint32_t* work_counter;
 };
 int pbs_supported(uint32_t N, uint32_t k);
 int launch_pbs(const PbsLaunch& p, cudaStream_t stream);

@@ -40,6 +40,7 @@ struct PbsArgs {
     int base_log, level, mode;
     uint64_t body_const;
     uint32_t count;
+    uint32_t* work_counter;    // device counter (zeroed before the launch): ciphertexts are handed out dynamically
 };
 
 // signed digit `lvl` (1-based) of x in O(1): raw digit plus the carry of the balanced representation of the
@@ -157,9 +158,15 @@ pbs_kernel(PbsArgs a) {
         }
     };
 
-    for (uint32_t ct = blockIdx.x; ct < a.count; ct += gridDim.x) {
-        const uint64_t* in = a.in + (size_t)ct * (a.n + 1);
+    // dynamic hand-out of ciphertexts: with small batches (multi-GPU shards) a static stride leaves SMs unevenly loaded
+    __shared__ uint32_t s_ct;
+    for (;;) {
         __syncthreads();
+        if (t == 0) s_ct = atomicAdd(a.work_counter, 1u);
+        __syncthreads();
+        const uint32_t ct = s_ct;
+        if (ct >= a.count) break;
+        const uint64_t* in = a.in + (size_t)ct * (a.n + 1);
         {   // acc = X^{-bhat} * (0, .., 0, LUT)
             const uint64_t* lut = a.luts + (size_t)a.lut_index[ct] * N;
             const uint32_t bhat = mod_switch(__ldg(in + a.n), LOGN + 1);
@@ -393,6 +400,11 @@ int launch_pbs(const PbsLaunch& p, cudaStream_t stream) {
     a.bsk = reinterpret_cast<const double2*>(p.bsk);
     a.tw = reinterpret_cast<const double2*>(p.tw);
     a.in = p.in; a.luts = p.luts; a.lut_index = p.lut_index; a.out = p.out;
+    a.work_counter = p.work_counter;
+    {
+        cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(uint32_t), stream);
+        if (e != cudaSuccess) return set_cuda_error(e, "cudaMemsetAsync(pbs work counter)");
+    }
     a.n = p.n; a.big_dim = p.big_dim; a.base_log = p.base_log; a.level = p.level; a.mode = p.mode; a.body_const = p.body_const;
     a.count = (uint32_t)p.count;
 #define TFX_PBS_CASE(LN, KK) if (p.N == (1u << LN) && p.k == KK) return launch_pbs_t<LN, KK>(a, p.sm_count, stream);
