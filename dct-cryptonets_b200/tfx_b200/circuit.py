@@ -294,6 +294,8 @@ class _Sym:
     shape: Tuple[int, ...]
     affine_only: bool = True                  # chain is a pure positive scaling (can be decoded without a table)
     affine_factor: float = 1.0
+    quant: Optional[QuantInfo] = None         # the chain ends in a QAT activation quantiser: values lie on this grid
+    pending_input: bool = False               # the raw float input, not quantised yet (its first consumer decides how)
 
 
 def _bits_for_range(lo: int, hi: int) -> int:
@@ -312,6 +314,41 @@ def _weight_bits(mod: nn.Module, n_bits: int) -> int:
 def _act_bits(mod: nn.Module, n_bits: int) -> int:
     v = getattr(mod, "act_bit_width", None)
     return v if isinstance(v, int) else n_bits
+
+
+def _act_quant_spec(mod: nn.Module) -> Optional[QuantInfo]:
+    """activation quantiser of a QAT module (QuantIdentity / QuantReLU, reference models/backbone.py:71-73,83,231,249,261,278):
+    scale and integer range as the module defines them (learned threshold), not calibrated.  Reads the compat shim
+    (compat/brevitas) or Brevitas' own accessors; None means 'no quantiser information' (treated like the float op)."""
+    if hasattr(mod, "tfx_act_quant"):
+        scale, lo, hi = mod.tfx_act_quant()
+        return QuantInfo(float(scale), int(lo), int(hi))
+    try:                                                       # Brevitas proper (untested here: not installable)
+        scale = float(mod.quant_act_scale())
+        bits = int(mod.quant_act_bit_width())
+        signed = bool(mod.is_quant_act_signed)
+        narrow = bool(getattr(mod, "is_quant_act_narrow_range", False))
+    except Exception:
+        return None
+    if signed:
+        return QuantInfo(scale, -(1 << (bits - 1)) + (1 if narrow else 0), (1 << (bits - 1)) - 1)
+    return QuantInfo(scale, 0, (1 << bits) - 1 - (1 if narrow else 0))
+
+
+def _weight_quant_spec(mod: nn.Module):
+    """(int32 weights, scale) of a QuantConv2d as the module defines them, or None"""
+    if hasattr(mod, "tfx_weight_quant"):
+        w, scale = mod.tfx_weight_quant()
+        return w.detach().cpu().numpy().astype(np.int32), float(scale)
+    try:                                                       # Brevitas proper (untested here)
+        qw = mod.quant_weight()
+        return qw.int().detach().cpu().numpy().astype(np.int32), float(qw.scale)
+    except Exception:
+        return None
+
+
+def _fake_quant_fn(q: QuantInfo):
+    return lambda y: torch.clamp(torch.round(y / q.scale), q.qmin, q.qmax) * q.scale
 
 
 class CircuitBuilder:
@@ -378,7 +415,10 @@ class CircuitBuilder:
         nb = out_bits if out_bits is not None else self.n_bits
         signed = bool(y_cal.min() < 0)
         qmax = (1 << (nb - 1)) - 1 if signed else (1 << nb) - 1
-        if forced_scale is None:
+        if forced_scale is None and sym.quant is not None:
+            # QAT: the module's own quantiser is the table's output grid (y already lies on it)
+            scale, qlo, qhi = sym.quant.scale, sym.quant.qmin, sym.quant.qmax
+        elif forced_scale is None:
             amax = float(np.abs(y_cal).max())
             scale = (amax / qmax) if amax > 0 else 1.0
             qlo, qhi = (-qmax if signed else 0), qmax
@@ -404,24 +444,28 @@ class CircuitBuilder:
         out_sym = None
         for node in graph.nodes:
             if node.op == "placeholder":
-                x = self.calib
-                amax = float(x.abs().max())
-                qmax = (1 << (self.n_bits - 1)) - 1
-                scale = amax / qmax if amax > 0 else 1.0
-                vid = self._new()
-                self.input_id = vid
-                self.input_quant = QuantInfo(scale, -qmax, qmax)
-                self.ints[vid] = np.clip(np.rint(x.numpy() / scale), -qmax, qmax).astype(np.int64)
-                self.qinfo[vid] = self.input_quant
-                env[node] = _Sym(vid, False, scale, [], tuple(x.shape[1:]))
+                env[node] = _Sym(-1, False, 1.0, [], tuple(self.calib.shape[1:]), pending_input=True)
             elif node.op == "call_module":
                 m = mods[node.target]
-                src = env[node.args[0]]
                 tname = type(m).__name__
+                aq = _act_quant_spec(m) if tname in ("QuantIdentity", "QuantReLU") else None
+                if env[node.args[0]].pending_input:
+                    # the input quantiser: a leading QuantIdentity defines it (QAT), otherwise n_bits symmetric from the calibration set
+                    env[node.args[0]] = self._quantize_input(aq if tname == "QuantIdentity" else None)
+                    if tname == "QuantIdentity" and aq is not None:
+                        env[node] = env[node.args[0]]
+                        continue
+                src = env[node.args[0]]
                 if isinstance(m, nn.Conv2d) or tname == "QuantConv2d":
                     env[node] = self._conv(node, m, src, node.args[0])
                 elif isinstance(m, nn.BatchNorm2d):
                     env[node] = self._chain(src, _bn_fn(m), False)
+                elif aq is not None:
+                    if not src.lin_is_acc:
+                        raise NotImplementedError("activation quantiser directly on a quantised tensor (needs a linear op first)")
+                    fn = _fake_quant_fn(aq) if tname == "QuantIdentity" else (lambda y, f=_fake_quant_fn(aq): f(torch.relu(y)))
+                    env[node] = self._chain(src, fn, False)
+                    env[node].quant = aq
                 elif isinstance(m, nn.ReLU) or tname == "QuantReLU":
                     env[node] = self._chain(src, torch.relu, False)
                 elif tname == "QuantIdentity" or isinstance(m, (nn.Identity, nn.Dropout)):
@@ -429,10 +473,14 @@ class CircuitBuilder:
                 elif isinstance(m, nn.AvgPool2d):
                     env[node] = self._avgpool(node, m, src, node.args[0])
                 elif isinstance(m, nn.Flatten):
-                    env[node] = _Sym(src.lin, src.lin_is_acc, src.scale, src.chain, (int(np.prod(src.shape)),), src.affine_only, src.affine_factor)
+                    env[node] = _Sym(src.lin, src.lin_is_acc, src.scale, src.chain, (int(np.prod(src.shape)),), src.affine_only, src.affine_factor,
+                                     src.quant)
                 else:
                     raise NotImplementedError(f"unsupported module {tname} at {node.target}")
             elif node.op == "call_function":
+                for arg in node.args:
+                    if isinstance(arg, fx.Node) and env[arg].pending_input:
+                        env[arg] = self._quantize_input(None)
                 fname = getattr(node.target, "__name__", str(node.target))
                 if fname in ("add", "iadd"):
                     env[node] = self._add(node, env[node.args[0]], env[node.args[1]], node.args[0], node.args[1])
@@ -440,7 +488,8 @@ class CircuitBuilder:
                     env[node] = self._chain(env[node.args[0]], torch.relu, False)
                 elif fname == "flatten":
                     src = env[node.args[0]]
-                    env[node] = _Sym(src.lin, src.lin_is_acc, src.scale, src.chain, (int(np.prod(src.shape)),), src.affine_only, src.affine_factor)
+                    env[node] = _Sym(src.lin, src.lin_is_acc, src.scale, src.chain, (int(np.prod(src.shape)),), src.affine_only, src.affine_factor,
+                                     src.quant)
                 else:
                     raise NotImplementedError(f"unsupported function {fname}")
             elif node.op == "output":
@@ -449,6 +498,19 @@ class CircuitBuilder:
             else:
                 raise NotImplementedError(f"unsupported fx node {node.op}")
         return self._finish(out_sym, out_key)
+
+    def _quantize_input(self, spec: Optional[QuantInfo]) -> _Sym:
+        x = self.calib
+        if spec is None:
+            amax = float(x.abs().max())
+            qmax = (1 << (self.n_bits - 1)) - 1
+            spec = QuantInfo(amax / qmax if amax > 0 else 1.0, -qmax, qmax)
+        vid = self._new()
+        self.input_id = vid
+        self.input_quant = spec
+        self.ints[vid] = np.clip(np.rint(x.numpy() / spec.scale), spec.qmin, spec.qmax).astype(np.int64)
+        self.qinfo[vid] = spec
+        return _Sym(vid, False, spec.scale, [], tuple(x.shape[1:]))
 
     def _chain(self, src: _Sym, fn, affine: bool, keep_affine: bool = False) -> _Sym:
         if not src.lin_is_acc:
@@ -461,11 +523,17 @@ class CircuitBuilder:
 
     def _conv(self, node, m, src: _Sym, src_key) -> _Sym:
         q = self._materialize(src_key, src)
-        wb = _weight_bits(m, self.n_bits)
-        wq_max = (1 << (wb - 1)) - 1
-        wf = m.weight.detach().to(torch.float64)
-        s_w = float(wf.abs().max()) / wq_max if float(wf.abs().max()) > 0 else 1.0
-        wq = torch.clamp(torch.round(wf / s_w), -wq_max, wq_max).numpy().astype(np.int32)
+        wspec = _weight_quant_spec(m) if type(m).__name__ == "QuantConv2d" else None
+        if wspec is not None:                                                # QAT: the module's own weight quantiser
+            wq, s_w = wspec
+        else:
+            wb = _weight_bits(m, self.n_bits)
+            wq_max = (1 << (wb - 1)) - 1
+            wf = m.weight.detach().to(torch.float64)
+            s_w = float(wf.abs().max()) / wq_max if float(wf.abs().max()) > 0 else 1.0
+            wq = torch.clamp(torch.round(wf / s_w), -wq_max, wq_max).numpy().astype(np.int32)
+        if getattr(m, "groups", 1) != 1:
+            raise NotImplementedError("grouped convolution")
         if m.bias is not None:
             raise NotImplementedError("conv bias (the reference models use bias=False)")
         stride = m.stride[0]; pad = m.padding[0]
