@@ -260,7 +260,9 @@ def run_gpu(args):
             "config": {"workload": WORKLOAD, "parallelism": f"layer-partitioned x{world}", "pbs_per_image": cnt["total"],
                        "pbs_tlu": cnt["tlu"], "pbs_bit": cnt["bit"], "conv_macs": circ.macs(),
                        "tlu_set": vars(tlu) if hasattr(tlu, "__dict__") else str(tlu), "bit_set": str(bit),
-                       "l2": "every layer tensor (>= 134 MB) and both bootstrapping keys exceed L2 (126 MB); no flush needed",
+                       "l2": (f"no flush: every lookup layer streams its ciphertext tensor ({min(int(np.prod(op.shape)) for op in circ.lookups() if int(np.prod(op.shape)) > 64) * ex.words * 8 / 1e6:.0f}"
+                              f"-{max(int(np.prod(op.shape)) for op in circ.lookups()) * ex.words * 8 / 1e6:.0f} MB) several times between two uses of any buffer, and the "
+                              f"{ex.keys.device_bytes / 1e6:.0f} MB of keys alternate per kernel; the working set per step exceeds L2 (126 MB)"),
                        "keygen_s": t_keygen, "key_bytes": ex.keys.device_bytes},
             "pbs_per_sec_per_gpu": cnt["total"] / dev_s / world,
             "e2e": {"value": e2e_s, "unit": UNIT, "h2d_bytes_per_step": host_in.numel() * 8, "d2h_bytes_per_step": host_out.numel() * 8},

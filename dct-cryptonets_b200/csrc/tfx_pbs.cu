@@ -22,9 +22,10 @@ template <int LOGN, int K> struct PbsCfg {
     static constexpr int TPF = M / 8;                    // threads per ciphertext (8 complex points each)
     static constexpr int G = K + 1;
     static constexpr int THREADS = TPF;
-    // accumulator + two transform buffers (one per interleaved transform) + node twiddle table
+    // accumulator + two transform buffers (one per interleaved transform) + node twiddle table + the hand-out slot
+    // (kept in the dynamic allocation: a static __shared__ word on top of a 227 KB dynamic limit is rejected)
     static constexpr size_t smem_bytes(int) {
-        return (size_t)G * N * 8 + (size_t)M * 16 * 2 + (size_t)M * 16;
+        return (size_t)G * N * 8 + (size_t)M * 16 * 2 + (size_t)M * 16 + 16;
     }
     static constexpr int MIN_BLOCKS = (LOGN <= 11) ? 2 : 1;
 };
@@ -72,6 +73,7 @@ pbs_kernel(PbsArgs a) {
     uint64_t* acc = reinterpret_cast<uint64_t*>(smem_raw);                    // [G][N]
     double2* bufs = reinterpret_cast<double2*>(acc + (size_t)G * N);          // [2][M] swizzled, alternate per transform
     double2* s_tw = bufs + 2 * M;                                             // [M]
+    volatile uint32_t* s_ct = reinterpret_cast<volatile uint32_t*>(s_tw + M);  // next ciphertext index (dynamic hand-out)
 
     const int t = threadIdx.x;
     auto sync = [] { __syncthreads(); };
@@ -159,12 +161,11 @@ pbs_kernel(PbsArgs a) {
     };
 
     // dynamic hand-out of ciphertexts: with small batches (multi-GPU shards) a static stride leaves SMs unevenly loaded
-    __shared__ uint32_t s_ct;
     for (;;) {
         __syncthreads();
-        if (t == 0) s_ct = atomicAdd(a.work_counter, 1u);
+        if (t == 0) *s_ct = atomicAdd(a.work_counter, 1u);
         __syncthreads();
-        const uint32_t ct = s_ct;
+        const uint32_t ct = *s_ct;
         if (ct >= a.count) break;
         const uint64_t* in = a.in + (size_t)ct * (a.n + 1);
         {   // acc = X^{-bhat} * (0, .., 0, LUT)

@@ -7,6 +7,7 @@ fallback: if the shared library or a CUDA device is missing the calls raise.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 import os
 from dataclasses import dataclass
 from typing import Optional, Sequence
@@ -155,6 +156,7 @@ class Context:
         h = C.c_void_p()
         _check(self.lib.tfx_ctx_create(device, C.c_void_p(stream), 0 if use_torch_stream else 1, C.byref(h)), "tfx_ctx_create")
         self.h = h
+        self._keysets = weakref.WeakSet()
 
     def set_stream(self, stream: torch.cuda.Stream):
         _check(self.lib.tfx_ctx_set_stream(self.h, C.c_void_p(stream.cuda_stream)), "tfx_ctx_set_stream")
@@ -164,6 +166,8 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
+            for ks in list(getattr(self, "_keysets", ())):       # key sets hold a pointer to the context: release them first
+                ks.close()
             self.lib.tfx_ctx_destroy(self.h)
             self.h = None
 
@@ -235,6 +239,7 @@ class KeySet:
 
     def __init__(self, ctx: Context, params: Sequence[PbsParams], handle):
         self.ctx, self.params, self.h = ctx, list(params), handle
+        ctx._keysets.add(self)
         self.big_dim = max(p.big_dim for p in params)           # the big LWE key; every set's GLWE key is a prefix of it
 
     # -- construction -------------------------------------------------------------------------------

@@ -19,7 +19,7 @@ from typing import Iterable, List, Optional, Sequence, Tuple
 from .binding import PbsParams
 
 SUPPORTED_KN = {1: (512, 1024, 2048, 4096), 2: (512, 1024, 2048)}
-DEFAULT_BIG_DIM = 4096      # big LWE key of the circuits compiled here (the table set is (k=1, N=4096))
+BIG_DIMS = (1024, 2048, 4096)   # candidate big LWE key dimensions (the table set is (k=1, N=big_dim)); smallest feasible wins
 
 
 def z_score(p_error: float) -> float:
@@ -183,10 +183,26 @@ def _bsk_candidates(k: int, N: int, n: int, budget_var: float) -> Optional[Tuple
     return None
 
 
-def pick_parameters(spec: CircuitNoiseSpec, big_dim: int = 4096, n_step: int = 16) -> Tuple[PbsParams, PbsParams, dict]:
-    """Search (n, gadgets) for the two PBS flavours under the noise constraints; minimise the cost model.
+def pick_parameters(spec: CircuitNoiseSpec, big_dim: Optional[int] = None, n_step: int = 16) -> Tuple[PbsParams, PbsParams, dict]:
+    """Search the big key dimension, (n, gadgets) for the two PBS flavours under the noise constraints; minimise the cost model.
 
-    Strategy: split each PBS-input budget between the amplified accumulator noise and the keyswitch/mod-switch
+    big_dim=None tries BIG_DIMS in ascending order and returns the first feasible set: every cost term (transform size,
+    keyswitch length, ciphertext bytes) grows with the big dimension, so the smallest feasible one is the cheapest
+    (tests/test_circuit_cpu.py checks it against the forced 4096 search).  For the 6-bit lookups of the headline circuit the
+    mod-switch noise at 2N = 4096 just fits p_error = 0.01, giving (k=1, N=2048)."""
+    if big_dim is None:
+        err = None
+        for bd in BIG_DIMS:
+            try:
+                return _pick_for_big_dim(spec, bd, n_step)
+            except ValueError as e:
+                err = e
+        raise err
+    return _pick_for_big_dim(spec, big_dim, n_step)
+
+
+def _pick_for_big_dim(spec: CircuitNoiseSpec, big_dim: int, n_step: int) -> Tuple[PbsParams, PbsParams, dict]:
+    """Strategy: split each PBS-input budget between the amplified accumulator noise and the keyswitch/mod-switch
     noise, enumerate n and (k, N), take the cheapest gadget meeting each sub-budget, keep the cheapest feasible
     pair.  The final answer is re-verified with the exact check."""
     z = z_score(spec.p_error)
@@ -197,7 +213,7 @@ def pick_parameters(spec: CircuitNoiseSpec, big_dim: int = 4096, n_step: int = 1
     tlu_shapes = [(1, big_dim)] if big_dim in SUPPORTED_KN[1] else []
     # the bit-extraction set may use a GLWE key that is a prefix of the big key (k*N <= big_dim): its sample-extracted
     # ciphertext, zero-padded, is a ciphertext under the big key; security and noise follow its own dimension k*N
-    bit_shapes = [(k, N) for k in (1, 2) for N in SUPPORTED_KN[k] if k * N <= big_dim and k * N >= 2048]
+    bit_shapes = [(k, N) for k in (1, 2) for N in SUPPORTED_KN[k] if k * N <= big_dim and k * N >= min(2048, big_dim)]
     for (kA, NA) in tlu_shapes:
         for nA in range(400, 1300, n_step):
             budget_tlu = (2.0 ** -(t_max + 2) / z) ** 2
@@ -271,7 +287,7 @@ def pick_parameters(spec: CircuitNoiseSpec, big_dim: int = 4096, n_step: int = 1
         raise ValueError("no TFHE parameter set satisfies the circuit's noise constraints (accumulators too wide?)")
     cost, tlu, bit, margin = best
     info = {
-        "z": z, "p_error": spec.p_error, "cost_model": cost, "worst_margin": margin,
+        "z": z, "p_error": spec.p_error, "cost_model": cost, "worst_margin": margin, "big_dim": big_dim,
         "tlu": {"sigma_pbs_out_log2": 0.5 * math.log2(var_pbs_out(tlu)), "sigma_ks_log2": 0.5 * math.log2(var_keyswitch(tlu, big_dim)),
                 "sigma_ms_log2": 0.5 * math.log2(var_modswitch(tlu)),
                 "sigma_fft_log2": 0.5 * math.log2(tlu.n * var_fft_extprod(tlu.k, tlu.N, tlu.bsk_base_log, tlu.bsk_level)),

@@ -112,7 +112,10 @@ def test_parameter_picker_meets_noise_constraints(tiny):
     m, calib, circ = tiny
     spec = circ.noise_spec()
     tlu, bit, info = P.pick_parameters(spec)
-    assert tlu.k * tlu.N == 4096 and bit.k * bit.N in (2048, 4096)       # the bit set may use a prefix of the big key
+    assert tlu.k * tlu.N == info["big_dim"] and bit.k * bit.N <= tlu.k * tlu.N      # the bit set may use a prefix of the big key
+    # the big key dimension is searched: forcing the largest one is feasible too but never cheaper
+    tlu4, bit4, _ = P.pick_parameters(spec, big_dim=4096)
+    assert tlu4.k * tlu4.N == 4096 and P._cost(spec, tlu4, bit4) >= P._cost(spec, tlu, bit)
     ok, margin = P._check(spec, tlu, bit, P.z_score(spec.p_error))
     assert ok and margin >= 1.0 and abs(info["z"] - 2.5758) < 1e-3
     # a smaller p_error must never yield cheaper parameters; an unreachable one must fail loudly

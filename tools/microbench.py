@@ -19,11 +19,17 @@ from tfx_b200.binding import Context, KeySet, PbsParams   # noqa: E402
 
 # the sets the picker returns for DCT-ResNet-20 / 24x16^2 / n_bits 5 / rounding 6 / p_error 0.01 (seed 0)
 DEFAULT_SETS = {
-    "tlu": PbsParams(n=752, k=1, N=4096, bsk_base_log=16, bsk_level=2, ksk_base_log=2, ksk_level=7,
-                     lwe_std=P.min_noise_std(752), glwe_std=P.min_noise_std(4096)),
-    # bit-extraction set: its GLWE key is the first k*N = 2048 bits of the 4096-bit big key
-    "bit": PbsParams(n=516, k=2, N=1024, bsk_base_log=23, bsk_level=1, ksk_base_log=2, ksk_level=5,
-                     lwe_std=P.min_noise_std(516), glwe_std=P.min_noise_std(2048)),
+    # big LWE key of 2048 bits (the picker's choice since the big dimension is searched, tfx_b200/params.py)
+    "tlu": PbsParams(n=768, k=1, N=2048, bsk_base_log=15, bsk_level=2, ksk_base_log=2, ksk_level=8,
+                     lwe_std=P.min_noise_std(768), glwe_std=P.min_noise_std(2048)),
+    "bit": PbsParams(n=492, k=2, N=1024, bsk_base_log=23, bsk_level=1, ksk_base_log=2, ksk_level=5,
+                     lwe_std=P.min_noise_std(492), glwe_std=P.min_noise_std(2048)),
+    # the sets of the earlier 4096-bit big key (profiles/r01_microbench_v1..v10): --sets tlu4096,bit4096
+    "tlu4096": PbsParams(n=752, k=1, N=4096, bsk_base_log=16, bsk_level=2, ksk_base_log=2, ksk_level=7,
+                         lwe_std=P.min_noise_std(752), glwe_std=P.min_noise_std(4096)),
+    # bit-extraction set whose GLWE key is the first k*N = 2048 bits of the 4096-bit big key
+    "bit4096": PbsParams(n=516, k=2, N=1024, bsk_base_log=23, bsk_level=1, ksk_base_log=2, ksk_level=5,
+                         lwe_std=P.min_noise_std(516), glwe_std=P.min_noise_std(2048)),
     "bit_k1": PbsParams(n=516, k=1, N=2048, bsk_base_log=23, bsk_level=1, ksk_base_log=2, ksk_level=5,
                         lwe_std=P.min_noise_std(516), glwe_std=P.min_noise_std(2048)),
     "bit_full": PbsParams(n=524, k=2, N=2048, bsk_base_log=24, bsk_level=1, ksk_base_log=2, ksk_level=5,
