@@ -342,27 +342,31 @@ class KeySet:
         return out
 
     # -- server ops ---------------------------------------------------------------------------------
+    # `ctx`: the context (stream + scratch) to launch on; defaults to the one the keys were made with.  A second context
+    # on the same device lets two independent batches run on two streams (executor.py, multi-GPU shards).
     def keyswitch(self, set_id: int, cts: torch.Tensor, shift: int = 0, body_offset: int = 0,
-                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                  out: Optional[torch.Tensor] = None, ctx: Optional[Context] = None) -> torch.Tensor:
         p = self.params[set_id]
+        ctx = ctx if ctx is not None else self.ctx
         cts = cts.contiguous().view(-1, self.big_dim + 1)
         B = cts.shape[0]
         if out is None:
-            out = self.ctx.empty_u64(B, p.n + 1)
-        _check(self.ctx.lib.tfx_keyswitch_batch(self.ctx.h, self.h, set_id, _dptr(cts), _dptr(out), B, shift,
-                                                body_offset & (2**64 - 1)), "tfx_keyswitch_batch")
+            out = ctx.empty_u64(B, p.n + 1)
+        _check(ctx.lib.tfx_keyswitch_batch(ctx.h, self.h, set_id, _dptr(cts), _dptr(out), B, shift,
+                                           body_offset & (2**64 - 1)), "tfx_keyswitch_batch")
         return out
 
     def pbs(self, set_id: int, cts: torch.Tensor, luts: torch.Tensor, lut_index: torch.Tensor, mode: int = 0,
-            body_const: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+            body_const: int = 0, out: Optional[torch.Tensor] = None, ctx: Optional[Context] = None) -> torch.Tensor:
         p = self.params[set_id]
+        ctx = ctx if ctx is not None else self.ctx
         cts = cts.contiguous().view(-1, p.n + 1)
         B = cts.shape[0]
         assert luts.shape[-1] == p.N and lut_index.dtype == torch.int32 and lut_index.numel() == B
         if out is None:
             assert mode == 0
-            out = self.ctx.empty_u64(B, self.big_dim + 1)
-        assert out.numel() == B * (self.big_dim + 1)
-        _check(self.ctx.lib.tfx_pbs_batch(self.ctx.h, self.h, set_id, _dptr(cts), _dptr(luts), _dptr(lut_index), _dptr(out), B,
-                                          mode, body_const & (2**64 - 1)), "tfx_pbs_batch")
+            out = ctx.empty_u64(B, self.big_dim + 1)
+        assert out.numel() == B * (self.big_dim + 1) and out.is_contiguous()
+        _check(ctx.lib.tfx_pbs_batch(ctx.h, self.h, set_id, _dptr(cts), _dptr(luts), _dptr(lut_index), _dptr(out), B,
+                                     mode, body_const & (2**64 - 1)), "tfx_pbs_batch")
         return out

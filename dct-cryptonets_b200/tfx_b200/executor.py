@@ -10,6 +10,7 @@ an all-gather over NCCL.
 """
 from __future__ import annotations
 
+import os
 import time
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
@@ -106,6 +107,15 @@ class CircuitExecutor:
         self._bit_luts: Dict[Tuple[int, int], Tuple[torch.Tensor, int]] = {}
         self._weights: Dict[int, torch.Tensor] = {}
         self._bias: Dict[int, torch.Tensor] = {}
+        # Two-stream lookup layers: a rank's share of a layer is split in two halves whose rounding chains are enqueued on
+        # two streams, so the second half's CTAs fill the SMs that the first half's last, partial wave leaves idle (and
+        # vice versa).  With W ranks a layer of 12 288 ciphertexts leaves 12 288 / W per kernel — a few waves only — and
+        # every one of the ~8 kernels of a chain would otherwise pay its own tail.  On by default for world_size > 1;
+        # TFX_SPLIT_STREAMS=0/1 overrides.  Results are identical (the halves are independent ciphertexts).
+        env = os.environ.get("TFX_SPLIT_STREAMS")
+        self.split_streams = (world_size > 1) if env is None else (env == "1")
+        self._side_stream: Optional[torch.cuda.Stream] = None
+        self._side_ctx: Optional[Context] = None
         self._prepare_constants()
 
     # ---- constants ------------------------------------------------------------------------------------------
@@ -176,6 +186,13 @@ class CircuitExecutor:
     def _channel_range(self, C: int) -> Tuple[int, int, int]:
         return channel_range(C, self.rank, self.world)
 
+    def _side(self) -> Tuple[torch.cuda.Stream, Context]:
+        if self._side_ctx is None:
+            self._side_stream = torch.cuda.Stream(self.ctx.device)
+            with torch.cuda.stream(self._side_stream):
+                self._side_ctx = Context(self.ctx.device.index)      # binds to the side stream; own scratch + hand-out counter
+        return self._side_stream, self._side_ctx
+
     def _gather(self, local: torch.Tensor, C: int, per: int, hw: int) -> torch.Tensor:
         return gather_channels(local, C, per, hw, self.world, self.pg)
 
@@ -242,13 +259,30 @@ class CircuitExecutor:
                 nloc = acc.shape[0]
                 if nloc > 0:
                     w = op.acc_bits
-                    for b in range(op.lsbs if circ.rounding_method == "exact" else 0):
-                        small = timed("ks_bit", nloc, lambda: keys.keyswitch(BIT_SET, acc, shift=w - b, body_offset=1 << 62))
-                        lut, c = self._bit_luts[(w, b)]
-                        timed("pbs_bit", nloc, lambda: keys.pbs(BIT_SET, small, lut, self._zero_idx[:nloc], mode=1, body_const=c, out=acc))
-                    small = timed("ks_tlu", nloc, lambda: keys.keyswitch(TLU_SET, acc))
-                    out = timed("pbs_tlu", nloc, lambda: keys.pbs(TLU_SET, small, self._luts[op.dst],
-                                                                  self._lut_index[op.dst][lo * H * W: hi * H * W]))
+                    lut_idx = self._lut_index[op.dst][lo * H * W: hi * H * W]
+                    out = ctx.empty_u64(nloc, words)
+
+                    def chain(c_, r0, r1):
+                        """rounding chain + table lookup of rows [r0, r1) of this rank's share, enqueued on c_'s stream"""
+                        a_, n_ = acc[r0:r1], r1 - r0
+                        for b in range(op.lsbs if circ.rounding_method == "exact" else 0):
+                            small = timed("ks_bit", n_, lambda: keys.keyswitch(BIT_SET, a_, shift=w - b, body_offset=1 << 62, ctx=c_))
+                            lut, c = self._bit_luts[(w, b)]
+                            timed("pbs_bit", n_, lambda: keys.pbs(BIT_SET, small, lut, self._zero_idx[:n_], mode=1, body_const=c, out=a_, ctx=c_))
+                        small = timed("ks_tlu", n_, lambda: keys.keyswitch(TLU_SET, a_, ctx=c_))
+                        timed("pbs_tlu", n_, lambda: keys.pbs(TLU_SET, small, self._luts[op.dst], lut_idx[r0:r1], out=out[r0:r1], ctx=c_))
+
+                    if self.split_streams and nloc >= 2:
+                        side, side_ctx = self._side()
+                        main = torch.cuda.current_stream(ctx.device)
+                        half = nloc // 2
+                        side.wait_stream(main)                       # acc / out are produced / allocated on the main stream
+                        chain(ctx, 0, half)
+                        with torch.cuda.stream(side):
+                            chain(side_ctx, half, nloc)
+                        main.wait_stream(side)
+                    else:
+                        chain(ctx, 0, nloc)
                     if stats is not None:
                         nb = op.lsbs if circ.rounding_method == "exact" else 0
                         stats.pbs_bit += nloc * nb; stats.pbs_tlu += nloc; stats.keyswitches += nloc * (nb + 1)

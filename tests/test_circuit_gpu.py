@@ -61,6 +61,25 @@ def test_tiny_circuit_matches_oracle_and_clear(gpu_ctx, oracle):
     assert stats.pbs_tlu == cnt["tlu"] and stats.pbs_bit == cnt["bit"] and stats.launches > 0
 
 
+def test_two_stream_lookup_layers_give_identical_ciphertexts(gpu_ctx):
+    """the multi-GPU executor splits a rank's share of every lookup layer over two streams (executor.py); forced on here
+    on one GPU: every output word must equal the single-stream run, repeatedly (a race would show up as a difference)"""
+    model, calib, circ = build(seed=2)
+    one = CircuitExecutor(circ, (TOY_TLU, TOY_BIT), ctx=gpu_ctx, input_std=2.0**-50)
+    one.split_streams = False
+    one.keygen(seed=7)
+    two = CircuitExecutor(circ, (TOY_TLU, TOY_BIT), ctx=gpu_ctx, input_std=2.0**-50)
+    two.split_streams = True
+    two.use_keys(one.keys)
+    for img in range(3):
+        q_in = C.quantize_input(circ, calib[img:img + 1].numpy())[0]
+        cts = one.encrypt(q_in, enc_seed=8 + img)
+        want = gpu_ctx.to_host_u64(one.run(cts))
+        for _ in range(2):
+            assert np.array_equal(gpu_ctx.to_host_u64(two.run(cts)), want)
+    assert two._side_ctx is not None and one._side_ctx is None
+
+
 def test_quantized_module_execute_matches_simulate(gpu_ctx):
     from tfx_b200.quantized_module import QuantizedModule
     torch.manual_seed(1)
