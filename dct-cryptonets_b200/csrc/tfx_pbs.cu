@@ -25,8 +25,18 @@ template <int LOGN, int K> struct PbsCfg {
     // accumulator + two transform buffers (one per interleaved transform) + node twiddle table + the hand-out slot
     // (kept in the dynamic allocation: a static __shared__ word on top of a 227 KB dynamic limit is rejected)
     static constexpr size_t smem_bytes(int) {
-        return (size_t)G * N * 8 + (size_t)M * 16 * 2 + (size_t)M * 16 + 16;
+        return (size_t)G * N * 8 + (size_t)M * 16 * (DUAL ? 2 : 1) + (size_t)M * 16 + 16;
     }
+    // Two transforms interleaved per thread (more ILP, one more buffer) or one at a time.  Measured (profiles/r01_pbs_experiments.md):
+    // interleaving wins 13 % for (k=1, N=2048, l=2) — four forward and two inverse transforms pair up — and loses 6 % for
+    // (k=2, N=1024, l=1), whose three forward / three inverse transforms leave an odd one out.
+#if defined(TFX_PBS_SINGLE)
+    static constexpr bool DUAL = false;
+#elif defined(TFX_PBS_DUAL)
+    static constexpr bool DUAL = true;
+#else
+    static constexpr bool DUAL = !(K == 2 && LOGN <= 10);
+#endif
     static constexpr int MIN_BLOCKS = (LOGN <= 11) ? 2 : 1;
 };
 
@@ -72,14 +82,14 @@ pbs_kernel(PbsArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* acc = reinterpret_cast<uint64_t*>(smem_raw);                    // [G][N]
     double2* bufs = reinterpret_cast<double2*>(acc + (size_t)G * N);          // [2][M] swizzled, alternate per transform
-    double2* s_tw = bufs + 2 * M;                                             // [M]
+    double2* s_tw = bufs + (C::DUAL ? 2 : 1) * M;                             // [M]
     volatile uint32_t* s_ct = reinterpret_cast<volatile uint32_t*>(s_tw + M);  // next ciphertext index (dynamic hand-out)
 
     const int t = threadIdx.x;
     auto sync = [] { __syncthreads(); };
     auto wsync = [] { __syncwarp(); };
     double2* bufa = bufs;
-    double2* bufb = bufs + M;
+    double2* bufb = C::DUAL ? bufs + M : bufs;
 
     for (int i = t; i < M; i += TPF) s_tw[i] = a.tw[i];
 
@@ -212,6 +222,16 @@ pbs_kernel(PbsArgs a) {
             };
 
             // forward transforms two at a time (independent streams interleaved in every thread)
+            if constexpr (!C::DUAL) {
+#pragma unroll 1
+                for (int f = 0; f < n_fwd; f++) {
+                    double2 xa[8], w[7];
+                    load_tw<LOGM, 0>(w, t, s_tw);
+                    load_digits(xa, f, ahat);
+                    fft_forward_regs2<LOGM, false>(xa, xa, w, t, bufa, bufb, s_tw, sync, wsync);
+                    mac(xa, f);
+                }
+            } else {
 #pragma unroll 1
             for (int f = 0; f + 1 < n_fwd; f += 2) {
                 double2 xa[8], xb[8], w[7];
@@ -233,6 +253,7 @@ pbs_kernel(PbsArgs a) {
                 fft_forward_regs2<LOGM, false>(xa, xa, w, t, bufa, bufb, s_tw, sync, wsync);
                 mac(xa, n_fwd - 1);
             }
+            }
 
             auto add_back = [&](const double2 (&x)[8], int c) {
                 uint64_t* ac = acc + (size_t)c * N;
@@ -248,6 +269,16 @@ pbs_kernel(PbsArgs a) {
                 }
             };
             // inverse transforms, two output components at a time
+            if constexpr (!C::DUAL) {
+#pragma unroll
+                for (int c = 0; c < G; c++) {
+                    double2 xa[8];
+#pragma unroll
+                    for (int e = 0; e < 8; e++) xa[e] = part[c][e];
+                    fft_inverse_regs2<LOGM, false>(xa, xa, t, bufa, bufb, s_tw, sync, wsync);
+                    add_back(xa, c);
+                }
+            } else {
 #pragma unroll
             for (int c = 0; c + 1 < G; c += 2) {
                 double2 xa[8], xb[8];
@@ -263,6 +294,7 @@ pbs_kernel(PbsArgs a) {
                 for (int e = 0; e < 8; e++) xa[e] = part[G - 1][e];
                 fft_inverse_regs2<LOGM, false>(xa, xa, t, bufa, bufb, s_tw, sync, wsync);
                 add_back(xa, G - 1);
+            }
             }
             __syncthreads();                                           // accumulator complete before the next rotation reads
         }
