@@ -253,6 +253,16 @@ def run_gpu(args):
         if os.path.exists(ppath):
             prof = json.load(open(ppath))
         total_kernel_s = sum(v[0] for v in ks.values()) or 1.0
+
+        def pbs_roofline(cls, p_):
+            s_, n_, u_ = ks.get(cls, (0.0, 0, 0))
+            if not n_:
+                return None
+            f_ = u_ * P.pbs_flops(p_)
+            return {"kernel": f"pbs_kernel<log2N={p_.N.bit_length() - 1},k={p_.k}> ({cls})", "bound": "fp64", "achieved": f_ / s_ / 1e12,
+                    "peak": dfma / 1e12, "unit": "TFLOP/s", "frac": f_ / s_ / dfma, "pbs_per_launch": u_ / n_, "avg_launch_ms": s_ / n_ * 1e3,
+                    "share_of_step": s_ / total_kernel_s, "pbs_per_s": u_ / s_,
+                    "traffic": (prof.get(cls, {}).get("dram_bytes_per_unit") or 0) * u_ / n_ or None}
         line = {
             "metric": METRIC, "value": dev_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_s * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
@@ -280,7 +290,10 @@ def run_gpu(args):
                         "frac": nl * P.bsk_bytes(dom_p) / sec / 1e9 / hbm_peak, "peak_source": peak_src,
                         "note": "algorithmic bootstrapping-key bytes per launch (one pass over the key serves the whole batch)"},
             },
+            "roofline_other_pbs_kernel": pbs_roofline("pbs_tlu" if dom == "pbs_bit" else "pbs_bit", tlu if dom == "pbs_bit" else bit),
             "kernel_breakdown_s_per_step": {k: v[0] / args.steps for k, v in ks.items()},
+            "kernel_breakdown_note": ("CUDA-event time per kernel class on the launching stream" +
+                                      ("; with N > 1 the two halves of a layer run on two streams, so class times overlap and sum to more than the step" if world > 1 else "")),
             "imac_peak_tmacs": imac / 1e12,
             "check": {"max_abs_deviation_from_clear": max_dev, "clear_output_span": span,
                       "note": "p_error=0.01 per PBS makes execute != clear by design; tests/ hold the bit-exact parity checks"},

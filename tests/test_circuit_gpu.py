@@ -80,6 +80,48 @@ def test_two_stream_lookup_layers_give_identical_ciphertexts(gpu_ctx):
     assert two._side_ctx is not None and one._side_ctx is None
 
 
+def test_qat_circuit_executes_like_the_clear_evaluator(gpu_ctx):
+    """a Brevitas-style QAT block (quantisers taken from the modules) through the CUDA executor: decrypted outputs
+    equal the clear integer evaluator under tight-noise parameters"""
+    import os, sys
+    compat = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dct-cryptonets_b200", "compat")
+    if compat not in sys.path:
+        sys.path.append(compat)
+    import brevitas.nn as qnn
+    from brevitas.quant import Int8ActPerTensorFloat, Int8WeightPerTensorFloat
+    qconv = dict(weight_bit_width=4, weight_quant=Int8WeightPerTensorFloat, bias=False, bias_quant=None, narrow_range=True)
+    qid = dict(bit_width=4, act_quant=Int8ActPerTensorFloat)
+
+    class Block(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.inp = qnn.QuantIdentity(return_quant_tensor=False, **qid)
+            self.c0 = qnn.QuantConv2d(3, 4, 1, **qconv); self.b0 = nn.BatchNorm2d(4); self.r0 = qnn.QuantReLU(bit_width=4)
+            self.C1 = qnn.QuantConv2d(4, 4, 3, padding=1, **qconv); self.BN1 = nn.BatchNorm2d(4); self.relu1 = qnn.QuantReLU(bit_width=4)
+            self.C2 = qnn.QuantConv2d(4, 4, 3, padding=1, **qconv); self.BN2 = nn.BatchNorm2d(4)
+            self.quant_out = qnn.QuantIdentity(return_quant_tensor=False, scaling_init=1.0, **qid)
+            self.relu2 = qnn.QuantReLU(bit_width=4)
+            self.pool = nn.AvgPool2d(2); self.q = qnn.QuantIdentity(return_quant_tensor=False, **qid); self.flat = nn.Flatten()
+
+        def forward(self, x):
+            x = self.r0(self.b0(self.c0(self.inp(x))))
+            out = self.quant_out(self.BN2(self.C2(self.relu1(self.BN1(self.C1(x))))))
+            return self.flat(self.q(self.pool(self.relu2(torch.add(out, x)))))
+
+    torch.manual_seed(3)
+    net = Block().eval()
+    calib = torch.randn(40, 3, 4, 4) * 0.6
+    circ = C.build_circuit(net, calib, n_bits=5, rounding_threshold_bits=6, p_error=0.01)
+    assert circ.input_quant.scale == 0.125 and not circ.output_is_acc
+    ex = CircuitExecutor(circ, (TOY_TLU, TOY_BIT), ctx=gpu_ctx, input_std=2.0**-50)
+    ex.keygen(seed=11)
+    for img in range(2):
+        q_in = C.quantize_input(circ, calib[img:img + 1].numpy())[0]
+        out = ex.run(ex.encrypt(q_in, enc_seed=12 + img))
+        clear = C.evaluate_clear(circ, q_in[None])[0]
+        assert np.array_equal(ex.decrypt(out).reshape(clear.shape), clear)
+
+
 def test_quantized_module_execute_matches_simulate(gpu_ctx):
     from tfx_b200.quantized_module import QuantizedModule
     torch.manual_seed(1)
