@@ -287,11 +287,9 @@ bool keyswitch_imma_ok(uint32_t big_dim, int base_log, int level) {
 static int launch_keyswitch_imma(const KsLaunch& p, cudaStream_t stream) {
     const uint32_t Kp = p.big_dim * p.level, kc = 32 * p.level, npad = ksk_npad(p.n);
     const size_t smem = (size_t)2 * KI_TM * (kc + 16);
-    static size_t configured = 0;
-    if (smem > configured) {
+    {   // per launch: the attribute is per device, and a process may drive several devices / host threads
         cudaError_t e = cudaFuncSetAttribute(keyswitch_imma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(keyswitch_imma)");
-        configured = smem;
     }
     ks_decompose_kernel<<<(unsigned)p.sm_count * 16, 256, 0, stream>>>(p.in, p.digits, (uint32_t)p.count, p.big_dim, p.base_log, p.level, p.shift);
     count_launch();
@@ -310,11 +308,9 @@ int launch_keyswitch(const KsLaunch& p, cudaStream_t stream) {
     if (p.ksk_bytes && p.digits && keyswitch_imma_ok(p.big_dim, p.base_log, p.level)) return launch_keyswitch_imma(p, stream);
     if (p.level < 1 || p.level > 16) return set_error(TFX_ERR_UNSUPPORTED, "keyswitch: ksk_level must be in 1..16");
     if (p.base_log < 1 || p.base_log > 31) return set_error(TFX_ERR_ARG, "keyswitch: base_log out of range");
-    static bool configured = false;
-    if (!configured) {
+    {
         cudaError_t e = cudaFuncSetAttribute(keyswitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KS_SMEM);
         if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(keyswitch)");
-        configured = true;
     }
     KsArgs a;
     a.ksk = p.ksk; a.corr = p.ksk + (size_t)p.big_dim * p.level * ksk_npad(p.n);

@@ -402,15 +402,12 @@ template <int LOGN, int K>
 static int launch_pbs_t(const PbsArgs& a, int sm_count, cudaStream_t stream) {
     using C = PbsCfg<LOGN, K>;
     size_t smem = C::smem_bytes((int)a.n);
-    static bool configured = false;
-    static int blocks_per_sm = 1;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(pbs_kernel<LOGN, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(pbs)");
-        configured = true;
-    }
+    int blocks_per_sm = 1;
     if (smem > 227 * 1024) return set_error(TFX_ERR_UNSUPPORTED, "pbs: shared memory footprint exceeds 227 KB");
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, pbs_kernel<LOGN, K>, C::THREADS, smem);
+    // per launch: the attribute is per device, and a process may drive several devices / host threads
+    cudaError_t e = cudaFuncSetAttribute(pbs_kernel<LOGN, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(pbs)");
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, pbs_kernel<LOGN, K>, C::THREADS, smem);
     if (e != cudaSuccess) return set_cuda_error(e, "occupancy(pbs)");
     if (blocks_per_sm < 1) return set_error(TFX_ERR_UNSUPPORTED, "pbs: kernel does not fit on an SM");
     unsigned grid = (unsigned)sm_count * blocks_per_sm;

@@ -142,6 +142,9 @@ def test_transform_loader_mirror_and_errors():
     tf = tl.get_composed_transform_dct_img(aug=False, filter_size=4, channels=24, dct_pattern="default", device="cpu")
     img = GOLDEN["c24_s16_f4.in"][0]
     assert_close_ulps(tf(img).numpy(), GOLDEN["c24_s16_f4.out"][0])
+    mgr = DP.SimpleDataManager(16, batch_size=1)                                   # same call chain as homomorphic_eval.py:110-122
+    tf_np = mgr.trans_loader.get_composed_transform_dct_np(aug=False, filter_size=4, channels=24, device="cpu")
+    assert torch.equal(tf_np(img), tf(img))
     with pytest.raises(NotImplementedError):
         tl.get_composed_transform_dct_img(aug=True)
     with pytest.raises(TypeError):
