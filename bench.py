@@ -313,7 +313,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="tfx", choices=["tfx", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=32)
+    ap.add_argument("--cpu-sample", type=int, default=256, help="ciphertexts per CPU sample step (about 10 s of host work on 16 threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
