@@ -48,8 +48,8 @@ class ConvOp:
     depthwise: bool
     in_shape: Tuple[int, int, int]
     out_shape: Tuple[int, int, int]
-    acc_bits: int = 0           # w
-    offset: int = 0             # added so the accumulator is unsigned: u = acc + offset in [0, 2^w)
+    acc_bits: int = 0           # w (one width per tensor, like Concrete's per-tensor bit-width assignment)
+    offset: object = 0          # int64 [Cout]: added per output channel so the accumulator is unsigned: u = acc + offset in [0, 2^w)
     lshift: int = 0
     raw_weight: Optional[np.ndarray] = None   # before the encoding shift
     kind: str = "conv"
@@ -63,7 +63,7 @@ class AddOp:
     dst: int
     shape: Tuple[int, int, int]
     acc_bits: int = 0
-    offset: int = 0
+    offset: object = 0          # int64 [C], see ConvOp.offset
     sa: int = 1                 # 2^lshift of operand a
     sb: int = 1
     kind: str = "add"
@@ -98,7 +98,7 @@ class Circuit:
     output_shape: Tuple[int, ...]
     output_is_acc: bool         # True: decrypt an accumulator (offset/width below); False: a TLU output
     output_width: int
-    output_offset: int
+    output_offset: object       # int64 [C] (per channel of the output accumulator) or 0
     output_scale: float         # real value = output_scale * integer
     n_bits: int
     rounding_bits: int
@@ -155,9 +155,9 @@ class Circuit:
             if op.kind == "conv":
                 k = "sum_pool" if op.depthwise else "conv2d"
                 lines.append(f"  %{op.dst} = {k}(%{op.src}) {{weight=i32{list(op.weight.shape)}, stride={op.stride}, pad={op.pad}, "
-                             f"lshift={op.lshift}, offset={op.offset}}} : eint<{op.acc_bits}>{list(op.out_shape)}   // {op.name}")
+                             f"lshift={op.lshift}, offset={_offset_text(op.offset)}}} : eint<{op.acc_bits}>{list(op.out_shape)}   // {op.name}")
             elif op.kind == "add":
-                lines.append(f"  %{op.dst} = add(%{op.a} * {op.sa}, %{op.b} * {op.sb}) {{offset={op.offset}}} : eint<{op.acc_bits}>{list(op.shape)}   // {op.name}")
+                lines.append(f"  %{op.dst} = add(%{op.a} * {op.sa}, %{op.b} * {op.sb}) {{offset={_offset_text(op.offset)}}} : eint<{op.acc_bits}>{list(op.shape)}   // {op.name}")
             else:
                 lines.append(f"  %{op.dst} = round_lsbs<{op.lsbs}>.table_lookup(%{op.src}) {{tables=i64{list(op.tables.shape)}}} : "
                              f"eint<{op.out_width}>{list(op.shape)}   // {op.name}")
@@ -177,16 +177,33 @@ def _int_conv(x: np.ndarray, op: ConvOp, weight: np.ndarray) -> np.ndarray:
     return np.rint(y.numpy()).astype(np.int64)
 
 
+def channel_offsets(offset, channels: int) -> np.ndarray:
+    """per-channel accumulator offsets as int64 [C] (a scalar means the same offset for every channel)"""
+    o = np.asarray(offset, dtype=np.int64)
+    return np.full(channels, int(o), dtype=np.int64) if o.ndim == 0 else o
+
+
+def _bcast_offset(offset):
+    o = np.asarray(offset, dtype=np.int64)
+    return o.reshape(1, -1, 1, 1) if o.ndim == 1 else o
+
+
+def _offset_text(offset) -> str:
+    o = np.asarray(offset).reshape(-1)
+    return str(int(o[0])) if o.min() == o.max() else f"[{int(o.min())}..{int(o.max())}]/channel"
+
+
 def quantize_input(circ: Circuit, x: np.ndarray) -> np.ndarray:
     q = np.rint(np.asarray(x, dtype=np.float64) / circ.input_quant.scale)
     return np.clip(q, circ.input_quant.qmin, circ.input_quant.qmax).astype(np.int64)
 
 
-def tlu_apply(op: TluOp, offset: int, acc: np.ndarray) -> np.ndarray:
-    """acc int64 [B][C][H][W] (true accumulator, before offset) -> q int64; models the padding-bit wrap."""
+def tlu_apply(op: TluOp, offset, acc: np.ndarray) -> np.ndarray:
+    """acc int64 [B][C][H][W] (true accumulator, before offset) -> q int64; models the padding-bit wrap.
+    offset: scalar or int64 [C]."""
     w, lsbs, t = op.acc_bits, op.lsbs, op.keep_bits
     half = (1 << (lsbs - 1)) if lsbs > 0 else 0
-    u = (acc + offset + half) & ((1 << (w + 1)) - 1)
+    u = (acc + _bcast_offset(offset) + half) & ((1 << (w + 1)) - 1)
     idx = u >> lsbs                                  # in [0, 2^(t+1))
     neg = idx >= (1 << t)
     idx = idx & ((1 << t) - 1)
@@ -196,7 +213,7 @@ def tlu_apply(op: TluOp, offset: int, acc: np.ndarray) -> np.ndarray:
     return np.where(neg, -q, q)
 
 
-def tlu_apply_noisy(op: TluOp, offset: int, acc: np.ndarray, exact: bool, norm2: float, fresh: bool, nm: "NoiseModel",
+def tlu_apply_noisy(op: TluOp, offset, acc: np.ndarray, exact: bool, norm2: float, fresh: bool, nm: "NoiseModel",
                     rng: np.random.Generator) -> np.ndarray:
     """Like tlu_apply, but every PBS decision sees the modelled ciphertext noise: the accumulator noise
     (weights x PBS output noise), the keyswitch + mod-switch noise at each PBS input and the output noise of every
@@ -205,7 +222,7 @@ def tlu_apply_noisy(op: TluOp, offset: int, acc: np.ndarray, exact: bool, norm2:
     lsb = 2.0 ** -(w + 1)                                            # torus fraction of one accumulator unit
     half = (1 << (lsbs - 1)) if (lsbs > 0 and exact) else 0
     v_src = nm.input_var if fresh else nm.var_tlu_out
-    x = (acc + offset + half).astype(np.float64) + rng.normal(0.0, np.sqrt(norm2 * v_src) / lsb, size=acc.shape)
+    x = (acc + _bcast_offset(offset) + half).astype(np.float64) + rng.normal(0.0, np.sqrt(norm2 * v_src) / lsb, size=acc.shape)
     if exact:
         for b in range(lsbs):
             # phase of (x << (w - b)) + 1/4 turn, in turns; bit b is its top bit
@@ -353,8 +370,9 @@ def _fake_quant_fn(q: QuantInfo):
 
 class CircuitBuilder:
     def __init__(self, model: nn.Module, calib: torch.Tensor, n_bits: int = 5, rounding_threshold_bits: int = 6,
-                 p_error: float = 0.01, range_margin: float = 0.0):
+                 p_error: float = 0.01, range_margin: float = 0.0, per_channel_offsets: bool = True):
         self.model = model.eval()
+        self.per_channel_offsets = per_channel_offsets
         self.n_bits, self.t, self.p_error, self.margin = n_bits, rounding_threshold_bits, p_error, range_margin
         self.calib = calib.detach().to(torch.float64).cpu()
         self.ops: List[object] = []
@@ -371,15 +389,29 @@ class CircuitBuilder:
 
     # ---- accumulator range / width -----------------------------------------------------------------------
     def _finish_acc(self, op, acc: np.ndarray):
-        lo, hi = int(acc.min()), int(acc.max())
-        if self.margin > 0:
-            m = int(math.ceil(self.margin * max(1, hi - lo)))
-            lo, hi = lo - m, hi + m
-        # choose w so that the rounded index still fits: hi - lo + half < 2^w
-        w = _bits_for_range(lo, hi)
-        while w > self.t and (hi - lo) + (1 << (w - self.t - 1)) >= (1 << w):
+        """One width per tensor.  per_channel_offsets (default): every channel is centred in [0, 2^w) on its own, so the width
+        only has to cover the widest channel span (times 1 + 2 * range_margin) instead of the union of all channel ranges —
+        often one bit (= one bit-extraction PBS per element) less — and every channel keeps equal slack below and above
+        (a channel aligned at 0 wraps below zero at the first noisy or out-of-calibration value).
+        per_channel_offsets=False: one tensor-wide offset, u = acc - min over the tensor."""
+        lo_c = acc.min(axis=(0, 2, 3)).astype(np.int64)
+        hi_c = acc.max(axis=(0, 2, 3)).astype(np.int64)
+        if not self.per_channel_offsets:
+            lo_c[:], hi_c[:] = lo_c.min(), hi_c.max()
+        span_c = hi_c - lo_c
+        span = int(span_c.max())
+        need = span + 2 * int(math.ceil(self.margin * max(1, span)))
+        # choose w so that the rounded index still fits: need + half < 2^w
+        w = _bits_for_range(0, need)
+        while w > self.t and need + (1 << (w - self.t - 1)) >= (1 << w):
             w += 1
-        op.acc_bits, op.offset = w, -lo
+        half = (1 << (w - self.t - 1)) if w > self.t else 0
+        if self.per_channel_offsets:
+            slack_c = ((1 << w) - half - 1 - span_c) // 2              # centre every channel: equal slack below and above
+            op.acc_bits, op.offset = w, slack_c - lo_c
+        else:
+            m = int(math.ceil(self.margin * max(1, span)))
+            op.acc_bits, op.offset = w, np.full(lo_c.shape, m - int(lo_c[0]), dtype=np.int64)
 
     # ---- table construction ------------------------------------------------------------------------------
     def _materialize(self, node_key, sym: _Sym, forced_scale: Optional[float] = None, out_bits: Optional[int] = None) -> int:
@@ -401,15 +433,16 @@ class CircuitBuilder:
         C = acc.shape[1]
         # float function per channel on every representable rounded accumulator value
         idx = np.arange(1 << keep, dtype=np.int64)
-        acc_vals = (idx << lsbs) - off                                       # value the index stands for
-        xin = torch.from_numpy(np.broadcast_to(acc_vals.reshape(1, 1, -1, 1), (1, C, 1 << keep, 1)).astype(np.float64) * sym.scale)
+        off = channel_offsets(off, C)
+        acc_vals = (idx[None, :] << lsbs) - off[:, None]                     # [C][2^keep]: value the index stands for, per channel
+        xin = torch.from_numpy((acc_vals.astype(np.float64) * sym.scale).reshape(1, C, 1 << keep, 1))
         y = xin
         for fn in sym.chain:
             y = fn(y)
         y = y.reshape(C, 1 << keep).numpy()
         # output quantiser: calibrate on the values the calibration set actually reaches
         half = (1 << (lsbs - 1)) if lsbs > 0 else 0
-        cal_idx = np.clip((acc + off + half) >> lsbs, 0, (1 << keep) - 1)
+        cal_idx = np.clip((acc + off.reshape(1, C, 1, 1) + half) >> lsbs, 0, (1 << keep) - 1)
         ch = np.arange(C).reshape(1, C, 1, 1)
         y_cal = y[np.broadcast_to(ch, cal_idx.shape), cal_idx]
         nb = out_bits if out_bits is not None else self.n_bits
@@ -638,9 +671,10 @@ def _bn_fn(m: nn.BatchNorm2d):
 
 
 def build_circuit(model: nn.Module, calib: torch.Tensor, n_bits: int = 5, rounding_threshold_bits: int = 6,
-                  p_error: float = 0.01, range_margin: float = 0.0, rounding_method: str = "exact") -> Circuit:
+                  p_error: float = 0.01, range_margin: float = 0.0, rounding_method: str = "exact",
+                  per_channel_offsets: bool = True) -> Circuit:
     if rounding_method not in ("exact", "approximate"):
         raise ValueError("rounding_method must be 'exact' or 'approximate'")
-    circ = CircuitBuilder(model, calib, n_bits, rounding_threshold_bits, p_error, range_margin).build()
+    circ = CircuitBuilder(model, calib, n_bits, rounding_threshold_bits, p_error, range_margin, per_channel_offsets).build()
     circ.rounding_method = rounding_method
     return circ

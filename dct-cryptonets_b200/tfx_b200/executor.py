@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from .binding import Context, KeySet, PbsParams, launch_count
-from .circuit import Circuit, ConvOp, AddOp, TluOp
+from .circuit import Circuit, ConvOp, AddOp, TluOp, channel_offsets
 
 MASK64 = (1 << 64) - 1
 TLU_SET, BIT_SET = 0, 1
@@ -125,9 +125,7 @@ class CircuitExecutor:
         for op in self.circ.ops:
             if op.kind == "conv":
                 self._weights[op.dst] = torch.from_numpy(np.ascontiguousarray(op.weight)).to(dev)
-                half = (1 << (self._lsbs_after(op) - 1)) if self._lsbs_after(op) > 0 else 0
-                bias = ((op.offset + half) << (63 - op.acc_bits)) & MASK64
-                self._bias[op.dst] = self.ctx.to_device_u64(np.full(op.out_shape[0], bias, dtype=np.uint64))
+                self._bias[op.dst] = self.ctx.to_device_u64(self._body_constants(op, op.out_shape[0]))
             elif op.kind == "tlu":
                 luts = lut_polynomials(op.tables, op.keep_bits, N_tlu, op.out_width)
                 self._luts[op.dst] = self.ctx.to_device_u64(luts)
@@ -140,6 +138,13 @@ class CircuitExecutor:
                         lut, c = bit_lut(op.acc_bits, b, N_bit)
                         self._bit_luts[key] = (self.ctx.to_device_u64(lut[None]), c)
         self._zero_idx = torch.zeros(max(int(np.prod(op.shape)) for op in self.circ.lookups()), dtype=torch.int32, device=dev)
+
+    def _body_constants(self, lin_op, channels: int) -> np.ndarray:
+        """u64 [C]: (offset_c + half LSB of the rounding that follows) at the accumulator's encoding, added to the body word"""
+        ls = self._lsbs_after(lin_op)
+        half = (1 << (ls - 1)) if ls > 0 else 0
+        offs = channel_offsets(lin_op.offset, channels)
+        return np.array([((int(o) + half) << (63 - lin_op.acc_bits)) & MASK64 for o in offs], dtype=np.uint64)
 
     def _lsbs_after(self, lin_op) -> int:
         """rounding bits removed by the lookup that consumes this accumulator (0 if it is the circuit output).
@@ -179,7 +184,8 @@ class CircuitExecutor:
         u = ((ph + (np.uint64(1) << (shift - np.uint64(1)))) >> shift) & np.uint64((1 << (w + 1)) - 1)
         u = u.astype(np.int64)
         if self.circ.output_is_acc:
-            return u - self.circ.output_offset
+            offs = channel_offsets(self.circ.output_offset, self.circ.output_shape[0] if len(self.circ.output_shape) > 1 else 1)
+            return u - (np.repeat(offs, u.size // offs.size) if offs.size > 1 else int(offs[0]))
         return np.where(u >= (1 << w), u - (1 << (w + 1)), u)      # signed two's complement in w+1 bits
 
     # ---- server side ---------------------------------------------------------------------------------------------
@@ -244,12 +250,16 @@ class CircuitExecutor:
             elif op.kind == "add":
                 C, H, W = op.shape
                 lo, hi, per = self._channel_range(C)
-                half = (1 << (self._lsbs_after(op) - 1)) if self._lsbs_after(op) > 0 else 0
-                const = ((op.offset + half) << (63 - op.acc_bits)) & MASK64
+                consts = self._body_constants(op, C)
                 if hi > lo:
                     a = vals[op.a][lo:hi].contiguous()
                     b = vals[op.b][lo:hi].contiguous()
-                    acc = timed("add", a.shape[0] * H * W, lambda: ctx.axpby(a, op.sa, b, op.sb, body_const=const))
+                    if len(set(int(v) for v in consts[lo:hi])) == 1:
+                        acc = timed("add", a.shape[0] * H * W, lambda: ctx.axpby(a, op.sa, b, op.sb, body_const=int(consts[lo])))
+                    else:                                            # per-channel offsets: one launch per channel (H*W ciphertexts each)
+                        acc = torch.empty_like(a)
+                        for c in range(hi - lo):
+                            timed("add", H * W, lambda: ctx.axpby(a[c], op.sa, b[c], op.sb, body_const=int(consts[lo + c]), out=acc[c]))
                 else:
                     acc = ctx.empty_u64(0, H, W, words)
                 acc_local[op.dst] = (acc.view(-1, words), lo, hi, per)

@@ -69,10 +69,19 @@ def decrypt_output(circ, keys: OracleKeys, cts: np.ndarray) -> np.ndarray:
     for i, p in enumerate(ph):
         u = ((int(p) + (1 << (62 - w))) >> (63 - w)) & ((1 << (w + 1)) - 1)
         if circ.output_is_acc:
-            out[i] = u - circ.output_offset
+            offs = np.asarray(circ.output_offset, dtype=np.int64).reshape(-1)          # scalar or one offset per output channel
+            out[i] = u - int(offs[0] if offs.size == 1 else offs[i // (ph.size // offs.size)])
         else:
             out[i] = u - (1 << (w + 1)) if u >= (1 << w) else u
     return out
+
+
+def _body_constants(offset, half: int, acc_bits: int, channels: int) -> np.ndarray:
+    """u64 [C]: (offset_c + half) at the accumulator's encoding; offset is a scalar or one value per channel"""
+    offs = np.asarray(offset, dtype=np.int64).reshape(-1)
+    if offs.size == 1:
+        offs = np.repeat(offs, channels)
+    return np.array([((int(o) + half) << (63 - acc_bits)) & MASK64 for o in offs], dtype=np.uint64)
 
 
 def run_circuit(circ, keys: OracleKeys, in_cts: np.ndarray, collect: Optional[Dict[int, np.ndarray]] = None,
@@ -88,16 +97,16 @@ def run_circuit(circ, keys: OracleKeys, in_cts: np.ndarray, collect: Optional[Di
         if op.kind == "conv":
             ls = lsbs_after.get(op.dst, 0)
             half = (1 << (ls - 1)) if ls > 0 else 0
-            bias = np.full(op.out_shape[0], ((op.offset + half) << (63 - op.acc_bits)) & MASK64, dtype=np.uint64)
+            bias = _body_constants(op.offset, half, op.acc_bits, op.out_shape[0])
             t0 = time.time()
             vals[op.dst] = O.conv2d(vals[op.src], op.weight, op.stride, op.pad, bias, depthwise=op.depthwise)
             t_lin += time.time() - t0
         elif op.kind == "add":
             ls = lsbs_after.get(op.dst, 0)
             half = (1 << (ls - 1)) if ls > 0 else 0
-            const = ((op.offset + half) << (63 - op.acc_bits)) & MASK64
+            consts = _body_constants(op.offset, half, op.acc_bits, op.shape[0])
             t0 = time.time()
-            vals[op.dst] = O.axpby(vals[op.a], op.sa, vals[op.b], op.sb, const)
+            vals[op.dst] = np.stack([O.axpby(vals[op.a][c], op.sa, vals[op.b][c], op.sb, int(consts[c])) for c in range(op.shape[0])])
             t_lin += time.time() - t0
         else:
             C, H, W = op.shape

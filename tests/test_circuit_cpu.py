@@ -62,8 +62,39 @@ def test_accumulators_fit_their_width_on_calibration(tiny):
     C.evaluate_clear(circ, q, collect=vals)
     for op in circ.ops:
         if op.kind in ("conv", "add"):
-            u = vals[op.dst] + op.offset
+            u = vals[op.dst] + C.channel_offsets(op.offset, vals[op.dst].shape[1]).reshape(1, -1, 1, 1)
             assert u.min() >= 0 and u.max() < (1 << op.acc_bits)
+
+
+def test_per_channel_offsets_are_centred_and_robust():
+    """One offset per channel, one width per tensor: every channel is centred in [0, 2^w) (equal slack on both sides — a channel
+    whose minimum sits at 0 wraps below zero at the first noisy or out-of-calibration value and returns a negated table entry),
+    fewer bit extractions than a tensor-wide offset, and the noise simulation on unseen images stays free of such wraps."""
+    torch.manual_seed(0)
+    model = resnet20_dct(24, 16).eval()
+    g = torch.Generator().manual_seed(0)
+    calib = torch.randn(40, 24, 16, 16, generator=g)
+    unseen = torch.randn(3, 24, 16, 16, generator=g).numpy()
+    per = C.build_circuit(model, calib, 5, 6, 0.01)
+    wide = C.build_circuit(model, calib, 5, 6, 0.01, per_channel_offsets=False)
+    assert per.pbs_count()["tlu"] == wide.pbs_count()["tlu"] and per.pbs_count()["bit"] < 0.97 * wide.pbs_count()["bit"]
+    vals = {}
+    C.evaluate_clear(per, C.quantize_input(per, calib.numpy()), collect=vals)
+    for op in per.ops:
+        if op.kind in ("conv", "add"):
+            u = vals[op.dst] + C.channel_offsets(op.offset, vals[op.dst].shape[1]).reshape(1, -1, 1, 1)
+            lo, hi = u.min(axis=(0, 2, 3)), ((1 << op.acc_bits) - 1) - u.max(axis=(0, 2, 3))
+            assert (lo >= 0).all() and (hi >= 0).all()
+            lsbs = max(0, op.acc_bits - 6)
+            assert (np.abs(lo - hi) <= (1 << lsbs) // 2 + 2).all()          # centred up to the rounding half and integer division
+    tlu, bit, _ = P.pick_parameters(per.noise_spec())
+    nm = C.NoiseModel.from_params(tlu, bit, tlu.glwe_std)
+    q = C.quantize_input(per, unseen)
+    clear = C.evaluate_clear(per, q)
+    span = int(clear.max() - clear.min())
+    for seed in range(2):
+        noisy = C.evaluate_clear(per, q, noise=nm, rng=np.random.default_rng(seed))
+        assert np.abs(noisy - clear).max() < 0.2 * span
 
 
 def test_rounding_semantics_of_tlu_apply():
