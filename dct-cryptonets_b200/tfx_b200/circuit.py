@@ -52,6 +52,7 @@ class ConvOp:
     offset: object = 0          # int64 [Cout]: added per output channel so the accumulator is unsigned: u = acc + offset in [0, 2^w)
     lshift: int = 0
     raw_weight: Optional[np.ndarray] = None   # before the encoding shift
+    chan_bits: Optional[np.ndarray] = None    # per_channel_widths: int64 [Cout], width w_c <= acc_bits of every channel (None: all acc_bits)
     kind: str = "conv"
 
 
@@ -66,6 +67,7 @@ class AddOp:
     offset: object = 0          # int64 [C], see ConvOp.offset
     sa: int = 1                 # 2^lshift of operand a
     sb: int = 1
+    chan_bits: Optional[np.ndarray] = None    # see ConvOp.chan_bits
     kind: str = "add"
 
 
@@ -80,11 +82,22 @@ class TluOp:
     tables: np.ndarray          # int64 [C][2^keep_bits] integer outputs q
     out: QuantInfo
     out_width: int = 0          # encoding width of the produced ciphertexts (delta = 2^(63 - out_width))
+    chan_bits: Optional[np.ndarray] = None   # per-channel widths of the source accumulator (None: acc_bits for every channel)
     kind: str = "tlu"
 
     @property
     def lsbs(self) -> int:
+        """bits removed from the widest channel (every channel when chan_bits is None)"""
         return self.acc_bits - self.keep_bits
+
+    def chan_widths(self) -> np.ndarray:
+        C = self.tables.shape[0]
+        return np.full(C, self.acc_bits, dtype=np.int64) if self.chan_bits is None else np.asarray(self.chan_bits, dtype=np.int64)
+
+    def chan_lsbs(self) -> np.ndarray:
+        """int64 [C]: bits the exact rounding removes per channel.  All channels share the encoding 2^(63 - acc_bits); a channel of
+        width w_c < acc_bits simply has fewer low bits to extract, and its table lookup reads the ciphertext scaled by 2^(acc_bits - w_c)."""
+        return np.maximum(self.chan_widths() - self.keep_bits, 0)
 
 
 @dataclass
@@ -112,7 +125,8 @@ class Circuit:
 
     def pbs_count(self) -> Dict[str, int]:
         tlu = sum(int(np.prod(op.shape)) for op in self.lookups())
-        bit = sum(int(np.prod(op.shape)) * op.lsbs for op in self.lookups()) if self.rounding_method == "exact" else 0
+        bit = (sum(int(np.prod(op.shape[1:])) * int(op.chan_lsbs().sum()) for op in self.lookups())
+               if self.rounding_method == "exact" else 0)
         return {"tlu": tlu, "bit": bit, "total": tlu + bit}
 
     def macs(self) -> int:
@@ -139,12 +153,13 @@ class Circuit:
             else:
                 norm2 = float(lin.sa ** 2 + lin.sb ** 2)
                 fresh = False
+            shift = int(op.acc_bits - op.chan_widths().min())         # narrowest channel: its table lookup amplifies the noise by 2^shift
             if self.rounding_method == "exact":
-                looks.append(RoundedLookup(op.acc_bits, op.keep_bits, max(norm2, 1.0), fresh, int(np.prod(op.shape))))
+                looks.append(RoundedLookup(op.acc_bits, op.keep_bits, max(norm2, 1.0), fresh, int(np.prod(op.shape)), shift))
             else:
                 # approximate: one t-bit lookup straight on the accumulator; the accumulator noise counts at the table's
                 # granularity (the low bits are signal that shifts the rounding threshold, not noise)
-                looks.append(RoundedLookup(op.keep_bits, op.keep_bits, max(norm2, 1.0), fresh, int(np.prod(op.shape))))
+                looks.append(RoundedLookup(op.keep_bits, op.keep_bits, max(norm2, 1.0), fresh, int(np.prod(op.shape)), shift))
         return CircuitNoiseSpec(looks, self.p_error, input_std)
 
     def to_text(self) -> str:
@@ -159,7 +174,9 @@ class Circuit:
             elif op.kind == "add":
                 lines.append(f"  %{op.dst} = add(%{op.a} * {op.sa}, %{op.b} * {op.sb}) {{offset={_offset_text(op.offset)}}} : eint<{op.acc_bits}>{list(op.shape)}   // {op.name}")
             else:
-                lines.append(f"  %{op.dst} = round_lsbs<{op.lsbs}>.table_lookup(%{op.src}) {{tables=i64{list(op.tables.shape)}}} : "
+                l_c = op.chan_lsbs()
+                lsbs_txt = str(op.lsbs) if l_c.min() == l_c.max() else f"{int(l_c.min())}..{int(l_c.max())}/channel"
+                lines.append(f"  %{op.dst} = round_lsbs<{lsbs_txt}>.table_lookup(%{op.src}) {{tables=i64{list(op.tables.shape)}}} : "
                              f"eint<{op.out_width}>{list(op.shape)}   // {op.name}")
         lines.append(f"  return %{self.output_id}")
         return "\n".join(lines)
@@ -198,13 +215,19 @@ def quantize_input(circ: Circuit, x: np.ndarray) -> np.ndarray:
     return np.clip(q, circ.input_quant.qmin, circ.input_quant.qmax).astype(np.int64)
 
 
+def _chan_view(a: np.ndarray) -> np.ndarray:
+    return np.asarray(a, dtype=np.int64).reshape(1, -1, 1, 1)
+
+
 def tlu_apply(op: TluOp, offset, acc: np.ndarray) -> np.ndarray:
     """acc int64 [B][C][H][W] (true accumulator, before offset) -> q int64; models the padding-bit wrap.
-    offset: scalar or int64 [C]."""
-    w, lsbs, t = op.acc_bits, op.lsbs, op.keep_bits
-    half = (1 << (lsbs - 1)) if lsbs > 0 else 0
-    u = (acc + _bcast_offset(offset) + half) & ((1 << (w + 1)) - 1)
-    idx = u >> lsbs                                  # in [0, 2^(t+1))
+    offset: scalar or int64 [C].  Widths / removed bits may differ per channel (TluOp.chan_bits)."""
+    t = op.keep_bits
+    w = _chan_view(op.chan_widths())
+    lsbs = _chan_view(op.chan_lsbs())
+    half = np.where(lsbs > 0, np.left_shift(1, np.maximum(lsbs - 1, 0)), 0)
+    u = (acc + _bcast_offset(offset) + half) & (np.left_shift(1, w + 1) - 1)
+    idx = np.right_shift(u, lsbs)                    # in [0, 2^(t+1))
     neg = idx >= (1 << t)
     idx = idx & ((1 << t) - 1)
     C = op.tables.shape[0]
@@ -217,20 +240,22 @@ def tlu_apply_noisy(op: TluOp, offset, acc: np.ndarray, exact: bool, norm2: floa
                     rng: np.random.Generator) -> np.ndarray:
     """Like tlu_apply, but every PBS decision sees the modelled ciphertext noise: the accumulator noise
     (weights x PBS output noise), the keyswitch + mod-switch noise at each PBS input and the output noise of every
-    extracted bit.  All quantities in units of the accumulator LSB (delta_w = 2^-(w+1) of the torus)."""
-    w, lsbs, t = op.acc_bits, op.lsbs, op.keep_bits
-    lsb = 2.0 ** -(w + 1)                                            # torus fraction of one accumulator unit
-    half = (1 << (lsbs - 1)) if (lsbs > 0 and exact) else 0
+    extracted bit.  All quantities in units of the accumulator LSB (delta_w = 2^-(w+1) of the torus, w = the tensor's width)."""
+    W, t = op.acc_bits, op.keep_bits
+    w_c = _chan_view(op.chan_widths()).astype(np.float64)
+    lsbs_c = _chan_view(op.chan_lsbs())
+    lsb = 2.0 ** -(W + 1)                                            # torus fraction of one accumulator unit
+    half = np.where((lsbs_c > 0) & exact, np.left_shift(1, np.maximum(lsbs_c - 1, 0)), 0)
     v_src = nm.input_var if fresh else nm.var_tlu_out
     x = (acc + _bcast_offset(offset) + half).astype(np.float64) + rng.normal(0.0, np.sqrt(norm2 * v_src) / lsb, size=acc.shape)
     if exact:
-        for b in range(lsbs):
-            # phase of (x << (w - b)) + 1/4 turn, in turns; bit b is its top bit
-            ph = x * 2.0 ** (w - b) * lsb + 0.25 + rng.normal(0.0, np.sqrt(nm.var_bit_in), size=acc.shape)
+        for b in range(int(lsbs_c.max())):
+            # phase of (x << (W - b)) + 1/4 turn, in turns; bit b is its top bit; only channels that still have bits to remove
+            ph = x * 2.0 ** (W - b) * lsb + 0.25 + rng.normal(0.0, np.sqrt(nm.var_bit_in), size=acc.shape)
             bit = (np.floor(ph * 2.0) % 2.0)
-            x = x - bit * (1 << b) + rng.normal(0.0, np.sqrt(nm.var_bit_out) / lsb, size=acc.shape)
-    # table lookup on t bits + padding: index = round(phase / delta_t)
-    ph = x * lsb + rng.normal(0.0, np.sqrt(nm.var_tlu_in), size=acc.shape)
+            x = np.where(lsbs_c > b, x - bit * (1 << b) + rng.normal(0.0, np.sqrt(nm.var_bit_out) / lsb, size=acc.shape), x)
+    # table lookup on t bits + padding of the ciphertext scaled by 2^(W - w_c): index = round(phase / delta_t)
+    ph = x * lsb * 2.0 ** (W - w_c) + rng.normal(0.0, np.sqrt(nm.var_tlu_in), size=acc.shape)
     idx = np.floor(ph * 2.0 ** (t + 1) + 0.5).astype(np.int64) & ((1 << (t + 1)) - 1)
     neg = idx >= (1 << t)
     idx = idx & ((1 << t) - 1)
@@ -370,9 +395,12 @@ def _fake_quant_fn(q: QuantInfo):
 
 class CircuitBuilder:
     def __init__(self, model: nn.Module, calib: torch.Tensor, n_bits: int = 5, rounding_threshold_bits: int = 6,
-                 p_error: float = 0.01, range_margin: float = 0.0, per_channel_offsets: bool = True):
+                 p_error: float = 0.01, range_margin: float = 0.0, per_channel_offsets: bool = True,
+                 per_channel_widths: bool = False):
         self.model = model.eval()
-        self.per_channel_offsets = per_channel_offsets
+        if per_channel_widths and not per_channel_offsets:
+            raise ValueError("per_channel_widths needs per_channel_offsets")
+        self.per_channel_offsets, self.per_channel_widths = per_channel_offsets, per_channel_widths
         self.n_bits, self.t, self.p_error, self.margin = n_bits, rounding_threshold_bits, p_error, range_margin
         self.calib = calib.detach().to(torch.float64).cpu()
         self.ops: List[object] = []
@@ -400,18 +428,29 @@ class CircuitBuilder:
             lo_c[:], hi_c[:] = lo_c.min(), hi_c.max()
         span_c = hi_c - lo_c
         span = int(span_c.max())
-        need = span + 2 * int(math.ceil(self.margin * max(1, span)))
-        # choose w so that the rounded index still fits: need + half < 2^w
-        w = _bits_for_range(0, need)
-        while w > self.t and need + (1 << (w - self.t - 1)) >= (1 << w):
-            w += 1
-        half = (1 << (w - self.t - 1)) if w > self.t else 0
+
+        def width_for(sp: int) -> int:
+            need = sp + 2 * int(math.ceil(self.margin * max(1, sp)))
+            w_ = _bits_for_range(0, need)
+            while w_ > self.t and need + (1 << (w_ - self.t - 1)) >= (1 << w_):       # the rounded index must still fit
+                w_ += 1
+            return w_
+
+        w = width_for(span)
+        op.acc_bits = w
         if self.per_channel_offsets:
-            slack_c = ((1 << w) - half - 1 - span_c) // 2              # centre every channel: equal slack below and above
-            op.acc_bits, op.offset = w, slack_c - lo_c
+            if self.per_channel_widths and w > self.t:
+                w_c = np.array([min(w, max(self.t, width_for(int(sp)))) for sp in span_c], dtype=np.int64)
+                if (w_c < w).any():
+                    op.chan_bits = w_c
+            else:
+                w_c = np.full(span_c.shape, w, dtype=np.int64)
+            half_c = np.where(w_c > self.t, np.left_shift(1, np.maximum(w_c - self.t - 1, 0)), 0)
+            slack_c = (np.left_shift(1, w_c) - half_c - 1 - span_c) // 2             # centre every channel: equal slack below and above
+            op.offset = slack_c - lo_c
         else:
             m = int(math.ceil(self.margin * max(1, span)))
-            op.acc_bits, op.offset = w, np.full(lo_c.shape, m - int(lo_c[0]), dtype=np.int64)
+            op.offset = np.full(lo_c.shape, m - int(lo_c[0]), dtype=np.int64)
 
     # ---- table construction ------------------------------------------------------------------------------
     def _materialize(self, node_key, sym: _Sym, forced_scale: Optional[float] = None, out_bits: Optional[int] = None) -> int:
@@ -429,20 +468,21 @@ class CircuitBuilder:
         acc = self.ints[sym.lin]                                             # [B][C][H][W]
         w, off = lin_op.acc_bits, lin_op.offset
         keep = min(w, self.t)
-        lsbs = w - keep
         C = acc.shape[1]
+        w_c = np.full(C, w, dtype=np.int64) if lin_op.chan_bits is None else np.asarray(lin_op.chan_bits, dtype=np.int64)
+        lsbs = np.maximum(w_c - keep, 0)                                     # [C] bits removed per channel
         # float function per channel on every representable rounded accumulator value
         idx = np.arange(1 << keep, dtype=np.int64)
         off = channel_offsets(off, C)
-        acc_vals = (idx[None, :] << lsbs) - off[:, None]                     # [C][2^keep]: value the index stands for, per channel
+        acc_vals = np.left_shift(idx[None, :], lsbs[:, None]) - off[:, None]  # [C][2^keep]: value the index stands for, per channel
         xin = torch.from_numpy((acc_vals.astype(np.float64) * sym.scale).reshape(1, C, 1 << keep, 1))
         y = xin
         for fn in sym.chain:
             y = fn(y)
         y = y.reshape(C, 1 << keep).numpy()
         # output quantiser: calibrate on the values the calibration set actually reaches
-        half = (1 << (lsbs - 1)) if lsbs > 0 else 0
-        cal_idx = np.clip((acc + off.reshape(1, C, 1, 1) + half) >> lsbs, 0, (1 << keep) - 1)
+        half = np.where(lsbs > 0, np.left_shift(1, np.maximum(lsbs - 1, 0)), 0)
+        cal_idx = np.clip(np.right_shift(acc + (off + half).reshape(1, C, 1, 1), lsbs.reshape(1, C, 1, 1)), 0, (1 << keep) - 1)
         ch = np.arange(C).reshape(1, C, 1, 1)
         y_cal = y[np.broadcast_to(ch, cal_idx.shape), cal_idx]
         nb = out_bits if out_bits is not None else self.n_bits
@@ -461,7 +501,8 @@ class CircuitBuilder:
             qlo, qhi = (-reach if signed else 0), reach
         tables = np.clip(np.rint(y / scale), qlo, qhi).astype(np.int64)
         vid = self._new()
-        op = TluOp(f"tlu_{vid}", sym.lin, vid, tuple(acc.shape[1:]), w, keep, tables, QuantInfo(scale, qlo, qhi))
+        op = TluOp(f"tlu_{vid}", sym.lin, vid, tuple(acc.shape[1:]), w, keep, tables, QuantInfo(scale, qlo, qhi),
+                   chan_bits=lin_op.chan_bits)
         self.ops.append(op)
         self.ints[vid] = tlu_apply(op, off, acc)
         self.qinfo[vid] = op.out
@@ -672,9 +713,10 @@ def _bn_fn(m: nn.BatchNorm2d):
 
 def build_circuit(model: nn.Module, calib: torch.Tensor, n_bits: int = 5, rounding_threshold_bits: int = 6,
                   p_error: float = 0.01, range_margin: float = 0.0, rounding_method: str = "exact",
-                  per_channel_offsets: bool = True) -> Circuit:
+                  per_channel_offsets: bool = True, per_channel_widths: bool = False) -> Circuit:
     if rounding_method not in ("exact", "approximate"):
         raise ValueError("rounding_method must be 'exact' or 'approximate'")
-    circ = CircuitBuilder(model, calib, n_bits, rounding_threshold_bits, p_error, range_margin, per_channel_offsets).build()
+    circ = CircuitBuilder(model, calib, n_bits, rounding_threshold_bits, p_error, range_margin, per_channel_offsets,
+                          per_channel_widths).build()
     circ.rounding_method = rounding_method
     return circ

@@ -116,6 +116,7 @@ class CircuitExecutor:
         self.split_streams = (world_size > 1) if env is None else (env == "1")
         self._side_stream: Optional[torch.cuda.Stream] = None
         self._side_ctx: Optional[Context] = None
+        self._perm: Dict[Tuple[int, int, int], Tuple[torch.Tensor, np.ndarray]] = {}
         self._prepare_constants()
 
     # ---- constants ------------------------------------------------------------------------------------------
@@ -140,22 +141,21 @@ class CircuitExecutor:
         self._zero_idx = torch.zeros(max(int(np.prod(op.shape)) for op in self.circ.lookups()), dtype=torch.int32, device=dev)
 
     def _body_constants(self, lin_op, channels: int) -> np.ndarray:
-        """u64 [C]: (offset_c + half LSB of the rounding that follows) at the accumulator's encoding, added to the body word"""
-        ls = self._lsbs_after(lin_op)
-        half = (1 << (ls - 1)) if ls > 0 else 0
+        """u64 [C]: (offset_c + half LSB of the rounding that follows, per channel) at the accumulator's encoding, added to the body word"""
+        ls = self._lsbs_after(lin_op, channels)
         offs = channel_offsets(lin_op.offset, channels)
-        return np.array([((int(o) + half) << (63 - lin_op.acc_bits)) & MASK64 for o in offs], dtype=np.uint64)
+        return np.array([((int(o) + ((1 << (int(l) - 1)) if l > 0 else 0)) << (63 - lin_op.acc_bits)) & MASK64 for o, l in zip(offs, ls)],
+                        dtype=np.uint64)
 
-    def _lsbs_after(self, lin_op) -> int:
-        """rounding bits removed by the lookup that consumes this accumulator (0 if it is the circuit output).
-        Decides the half-LSB offset folded into the accumulator: in approximate mode the LUT's own half-box rotation
+    def _lsbs_after(self, lin_op, channels: int) -> np.ndarray:
+        """int64 [C]: rounding bits removed, per channel, by the lookup that consumes this accumulator (0 if it is the circuit
+        output).  Decides the half-LSB offset folded into the accumulator: in approximate mode the LUT's own half-box rotation
         already rounds to nearest, so no offset is added."""
-        if self.circ.rounding_method != "exact":
-            return 0
-        for op in self.circ.ops:
-            if op.kind == "tlu" and op.src == lin_op.dst:
-                return op.lsbs
-        return 0
+        if self.circ.rounding_method == "exact":
+            for op in self.circ.ops:
+                if op.kind == "tlu" and op.src == lin_op.dst:
+                    return op.chan_lsbs()
+        return np.zeros(channels, dtype=np.int64)
 
     # ---- keys ------------------------------------------------------------------------------------------------
     def keygen(self, seed=1, keep_standard_bsk: bool = False) -> float:
@@ -191,6 +191,15 @@ class CircuitExecutor:
     # ---- server side ---------------------------------------------------------------------------------------------
     def _channel_range(self, C: int) -> Tuple[int, int, int]:
         return channel_range(C, self.rank, self.world)
+
+    def _sorted_rows(self, dst: int, lo: int, hi: int, w_c: np.ndarray, hw: int):
+        """(device permutation sorted row -> original row, channel order) for a lookup layer with per-channel widths"""
+        key = (dst, lo, hi)
+        if key not in self._perm:
+            order = np.argsort(-w_c, kind="stable")
+            perm = (order[:, None] * hw + np.arange(hw)[None, :]).reshape(-1).astype(np.int64)
+            self._perm[key] = (torch.from_numpy(perm).to(self.ctx.device), order)
+        return self._perm[key]
 
     def _side(self) -> Tuple[torch.cuda.Stream, Context]:
         if self._side_ctx is None:
@@ -269,18 +278,48 @@ class CircuitExecutor:
                 nloc = acc.shape[0]
                 if nloc > 0:
                     w = op.acc_bits
-                    lut_idx = self._lut_index[op.dst][lo * H * W: hi * H * W]
-                    out = ctx.empty_u64(nloc, words)
+                    hw = H * W
+                    exact = circ.rounding_method == "exact"
+                    lut_idx = self._lut_index[op.dst][lo * hw: hi * hw]
+                    w_c = op.chan_widths()[lo:hi]
+                    l_c = op.chan_lsbs()[lo:hi] if exact else np.zeros(hi - lo, dtype=np.int64)
+                    uniform = bool((w_c == w).all())
+                    if uniform:
+                        src, out, idx_rows = acc, ctx.empty_u64(nloc, words), lut_idx
+                        steps = [nloc] * (op.lsbs if exact else 0)                  # rows [0, steps[b]) take part in extraction step b
+                        segments = [(0, nloc, w)]                                  # (row range, width) for the table lookup's keyswitch
+                    else:
+                        # per-channel widths: every channel removes only its own low bits.  Rows are sorted by channel width
+                        # (widest first), so the rows still active in step b are a prefix and equal-width rows are contiguous.
+                        perm_d, order = self._sorted_rows(op.dst, lo, hi, w_c, hw)
+                        src = acc.index_select(0, perm_d)
+                        idx_rows = lut_idx.index_select(0, perm_d)
+                        out = ctx.empty_u64(nloc, words)
+                        l_s, w_s = l_c[order], w_c[order]
+                        steps = [hw * int((l_s > b).sum()) for b in range(int(l_s.max()))]
+                        segments, c0 = [], 0
+                        for c1 in range(1, len(w_s) + 1):
+                            if c1 == len(w_s) or w_s[c1] != w_s[c0]:
+                                segments.append((c0 * hw, c1 * hw, int(w_s[c0])))
+                                c0 = c1
+                    n_small = self.params[TLU_SET].n + 1
 
                     def chain(c_, r0, r1):
                         """rounding chain + table lookup of rows [r0, r1) of this rank's share, enqueued on c_'s stream"""
-                        a_, n_ = acc[r0:r1], r1 - r0
-                        for b in range(op.lsbs if circ.rounding_method == "exact" else 0):
+                        for b, nb in enumerate(steps):
+                            e_ = min(r1, nb)
+                            if e_ <= r0:
+                                break
+                            a_, n_ = src[r0:e_], e_ - r0
                             small = timed("ks_bit", n_, lambda: keys.keyswitch(BIT_SET, a_, shift=w - b, body_offset=1 << 62, ctx=c_))
                             lut, c = self._bit_luts[(w, b)]
                             timed("pbs_bit", n_, lambda: keys.pbs(BIT_SET, small, lut, self._zero_idx[:n_], mode=1, body_const=c, out=a_, ctx=c_))
-                        small = timed("ks_tlu", n_, lambda: keys.keyswitch(TLU_SET, a_, ctx=c_))
-                        timed("pbs_tlu", n_, lambda: keys.pbs(TLU_SET, small, self._luts[op.dst], lut_idx[r0:r1], out=out[r0:r1], ctx=c_))
+                        small = c_.empty_u64(r1 - r0, n_small)
+                        for s0, s1, wv in segments:                                # one keyswitch per width: the ciphertext is scaled by 2^(w - wv)
+                            g0, g1 = max(s0, r0), min(s1, r1)
+                            if g1 > g0:
+                                timed("ks_tlu", g1 - g0, lambda: keys.keyswitch(TLU_SET, src[g0:g1], shift=w - wv, out=small[g0 - r0: g1 - r0], ctx=c_))
+                        timed("pbs_tlu", r1 - r0, lambda: keys.pbs(TLU_SET, small, self._luts[op.dst], idx_rows[r0:r1], out=out[r0:r1], ctx=c_))
 
                     if self.split_streams and nloc >= 2:
                         side, side_ctx = self._side()
@@ -293,9 +332,12 @@ class CircuitExecutor:
                         main.wait_stream(side)
                     else:
                         chain(ctx, 0, nloc)
+                    if not uniform:                                  # back to channel order: out[perm[i]] = sorted_out[i]
+                        unsorted = torch.empty_like(out)
+                        unsorted.index_copy_(0, perm_d, out)
+                        out = unsorted
                     if stats is not None:
-                        nb = op.lsbs if circ.rounding_method == "exact" else 0
-                        stats.pbs_bit += nloc * nb; stats.pbs_tlu += nloc; stats.keyswitches += nloc * (nb + 1)
+                        stats.pbs_bit += hw * int(l_c.sum()); stats.pbs_tlu += nloc; stats.keyswitches += hw * int(l_c.sum()) + nloc
                 else:
                     out = ctx.empty_u64(0, words)
                 del acc

@@ -102,6 +102,7 @@ class RoundedLookup:
     weight_norm2: float    # sum of squared integer weights feeding one accumulator element (inputs = PBS outputs)
     fresh_inputs: bool = False   # inputs are fresh encryptions instead of PBS outputs
     count: int = 0         # elements (for the cost model)
+    tlu_shift: int = 0     # per-channel widths: the narrowest channel's table lookup reads the ciphertext scaled by 2^tlu_shift
 
 
 @dataclass
@@ -129,7 +130,7 @@ def _check(spec: CircuitNoiseSpec, tlu: PbsParams, bit: PbsParams, z: float) -> 
             worst = min(worst, margin)
             if margin < 1.0:
                 return False, worst
-        v = v_acc + max(0, w - t) * vB + v_in_tlu
+        v = (v_acc + max(0, w - t) * vB) * 4.0 ** lk.tlu_shift + v_in_tlu
         margin = 2.0 ** -(t + 2) / (z * math.sqrt(v))
         worst = min(worst, margin)
         if margin < 1.0:

@@ -76,12 +76,15 @@ def decrypt_output(circ, keys: OracleKeys, cts: np.ndarray) -> np.ndarray:
     return out
 
 
-def _body_constants(offset, half: int, acc_bits: int, channels: int) -> np.ndarray:
-    """u64 [C]: (offset_c + half) at the accumulator's encoding; offset is a scalar or one value per channel"""
+def _body_constants(offset, lsbs_c, acc_bits: int, channels: int) -> np.ndarray:
+    """u64 [C]: (offset_c + half LSB of the rounding that follows, per channel) at the accumulator's encoding;
+    offset is a scalar or one value per channel, lsbs_c None (no rounding follows) or int64 [C]"""
     offs = np.asarray(offset, dtype=np.int64).reshape(-1)
     if offs.size == 1:
         offs = np.repeat(offs, channels)
-    return np.array([((int(o) + half) << (63 - acc_bits)) & MASK64 for o in offs], dtype=np.uint64)
+    ls = np.zeros(channels, dtype=np.int64) if lsbs_c is None else np.asarray(lsbs_c, dtype=np.int64)
+    return np.array([((int(o) + ((1 << (int(l) - 1)) if l > 0 else 0)) << (63 - acc_bits)) & MASK64 for o, l in zip(offs, ls)],
+                    dtype=np.uint64)
 
 
 def run_circuit(circ, keys: OracleKeys, in_cts: np.ndarray, collect: Optional[Dict[int, np.ndarray]] = None,
@@ -91,20 +94,16 @@ def run_circuit(circ, keys: OracleKeys, in_cts: np.ndarray, collect: Optional[Di
     words = in_cts.shape[-1]
     vals = {circ.input_id: in_cts.reshape(*circ.input_shape, words)}
     exact = getattr(circ, "rounding_method", "exact") == "exact"
-    lsbs_after = {op.src: op.lsbs for op in circ.ops if op.kind == "tlu"} if exact else {}
+    lsbs_after = {op.src: op.chan_lsbs() for op in circ.ops if op.kind == "tlu"} if exact else {}
     t_lin = t_ks = t_pbs = 0.0
     for op in circ.ops:
         if op.kind == "conv":
-            ls = lsbs_after.get(op.dst, 0)
-            half = (1 << (ls - 1)) if ls > 0 else 0
-            bias = _body_constants(op.offset, half, op.acc_bits, op.out_shape[0])
+            bias = _body_constants(op.offset, lsbs_after.get(op.dst), op.acc_bits, op.out_shape[0])
             t0 = time.time()
             vals[op.dst] = O.conv2d(vals[op.src], op.weight, op.stride, op.pad, bias, depthwise=op.depthwise)
             t_lin += time.time() - t0
         elif op.kind == "add":
-            ls = lsbs_after.get(op.dst, 0)
-            half = (1 << (ls - 1)) if ls > 0 else 0
-            consts = _body_constants(op.offset, half, op.acc_bits, op.shape[0])
+            consts = _body_constants(op.offset, lsbs_after.get(op.dst), op.acc_bits, op.shape[0])
             t0 = time.time()
             vals[op.dst] = np.stack([O.axpby(vals[op.a][c], op.sa, vals[op.b][c], op.sb, int(consts[c])) for c in range(op.shape[0])])
             t_lin += time.time() - t0
@@ -112,18 +111,31 @@ def run_circuit(circ, keys: OracleKeys, in_cts: np.ndarray, collect: Optional[Di
             C, H, W = op.shape
             acc = np.ascontiguousarray(vals[op.src].reshape(-1, words)).copy()
             w = op.acc_bits
-            for b in range(op.lsbs if exact else 0):
+            # widths may differ per channel (TluOp.chan_bits): all channels share the encoding 2^(63 - w); channel c extracts
+            # only its own chan_lsbs[c] low bits and its table lookup keyswitches the ciphertext scaled by 2^(w - w_c)
+            w_c = op.chan_widths() if hasattr(op, "chan_widths") else np.full(C, w, dtype=np.int64)
+            l_c = op.chan_lsbs() if hasattr(op, "chan_lsbs") else np.full(C, op.lsbs, dtype=np.int64)
+            hw = H * W
+            row_lsbs = np.repeat(l_c, hw)
+            for b in range(int(l_c.max()) if exact else 0):
+                rows = np.nonzero(row_lsbs > b)[0]
+                sub = np.ascontiguousarray(acc[rows])
                 t0 = time.time()
-                small = O.keyswitch(keys.ksk[1], acc, bit_p.ksk_base_log, bit_p.ksk_level, shift=w - b, body_offset=1 << 62)
+                small = O.keyswitch(keys.ksk[1], sub, bit_p.ksk_base_log, bit_p.ksk_level, shift=w - b, body_offset=1 << 62)
                 t1 = time.time()
                 c = 1 << (62 - w + b)
                 lut = np.full((1, bit_p.N), (-c) & MASK64, dtype=np.uint64)
-                O.pbs(keys.bsk_f[1], bit_p.bsk_base_log, small, lut, np.zeros(acc.shape[0], np.uint32), mode=1, body_const=c, out=acc,
+                O.pbs(keys.bsk_f[1], bit_p.bsk_base_log, small, lut, np.zeros(sub.shape[0], np.uint32), mode=1, body_const=c, out=sub,
                       big_dim=words - 1)
+                acc[rows] = sub
                 t2 = time.time()
                 t_ks += t1 - t0; t_pbs += t2 - t1
             t0 = time.time()
-            small = O.keyswitch(keys.ksk[0], acc, tlu_p.ksk_base_log, tlu_p.ksk_level)
+            small = np.empty((acc.shape[0], tlu_p.n + 1), dtype=np.uint64)
+            row_w = np.repeat(w_c, hw)
+            for wv in np.unique(w_c):
+                rows = np.nonzero(row_w == wv)[0]
+                small[rows] = O.keyswitch(keys.ksk[0], np.ascontiguousarray(acc[rows]), tlu_p.ksk_base_log, tlu_p.ksk_level, shift=int(w - wv))
             t1 = time.time()
             luts = np.stack([lut_poly(op.tables[c], op.keep_bits, tlu_p.N, op.out_width) for c in range(C)])
             idx = np.repeat(np.arange(C, dtype=np.uint32), H * W)

@@ -61,6 +61,36 @@ def test_tiny_circuit_matches_oracle_and_clear(gpu_ctx, oracle):
     assert stats.pbs_tlu == cnt["tlu"] and stats.pbs_bit == cnt["bit"] and stats.launches > 0
 
 
+def test_per_channel_widths_match_oracle_and_clear(gpu_ctx, oracle):
+    """opt-in per-channel accumulator widths (width-sorted rows, one table-lookup keyswitch per width, gather / scatter): GPU
+    ciphertexts == oracle circuit word for word, decrypted == clear evaluator; also with the two-stream split forced on"""
+    from oracle import circuit_oracle as CO
+    torch.manual_seed(4)
+    net = nn.Sequential(nn.Conv2d(3, 5, 1, bias=False), nn.BatchNorm2d(5), nn.ReLU(), ResidualBlock(5, 5, False),
+                        ResidualBlock(5, 7, True), nn.AvgPool2d(2), nn.Flatten()).eval()
+    for m in net.modules():
+        if isinstance(m, nn.BatchNorm2d):
+            m.weight.data = torch.linspace(0.2, 2.0, m.num_features)
+            m.bias.data = torch.linspace(-0.5, 0.5, m.num_features)
+    calib = torch.randn(32, 3, 4, 4)
+    circ = C.build_circuit(net, calib, n_bits=5, rounding_threshold_bits=6, p_error=0.01, per_channel_widths=True)
+    assert any(op.chan_bits is not None and len(set(op.chan_bits.tolist())) > 1 for op in circ.lookups())
+    ex = CircuitExecutor(circ, (TOY_TLU, TOY_BIT), ctx=gpu_ctx, input_std=2.0**-50)
+    ex.keygen(seed=13)
+    q_in = C.quantize_input(circ, calib[:1].numpy())[0]
+    cts = ex.encrypt(q_in, enc_seed=14)
+    stats = RunStats()
+    got = gpu_ctx.to_host_u64(ex.run(cts, stats))
+    keys = CO.OracleKeys((TOY_TLU, TOY_BIT), 13)
+    ref = CO.run_circuit(circ, keys, CO.encrypt_input(circ, keys, q_in, 2.0**-50, 14))
+    assert np.array_equal(got, ref)
+    clear = C.evaluate_clear(circ, q_in[None])[0]
+    assert np.array_equal(CO.decrypt_output(circ, keys, ref).reshape(clear.shape), clear)
+    assert stats.pbs_bit == circ.pbs_count()["bit"]
+    ex.split_streams = True
+    assert np.array_equal(gpu_ctx.to_host_u64(ex.run(cts)), ref)
+
+
 def test_two_stream_lookup_layers_give_identical_ciphertexts(gpu_ctx):
     """the multi-GPU executor splits a rank's share of every lookup layer over two streams (executor.py); forced on here
     on one GPU: every output word must equal the single-stream run, repeatedly (a race would show up as a difference)"""
