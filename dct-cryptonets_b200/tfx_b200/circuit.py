@@ -396,8 +396,10 @@ def _fake_quant_fn(q: QuantInfo):
 class CircuitBuilder:
     def __init__(self, model: nn.Module, calib: torch.Tensor, n_bits: int = 5, rounding_threshold_bits: int = 6,
                  p_error: float = 0.01, range_margin: float = 0.0, per_channel_offsets: bool = True,
-                 per_channel_widths: bool = False):
+                 per_channel_widths: Optional[bool] = None):
         self.model = model.eval()
+        if per_channel_widths is None:
+            per_channel_widths = per_channel_offsets
         if per_channel_widths and not per_channel_offsets:
             raise ValueError("per_channel_widths needs per_channel_offsets")
         self.per_channel_offsets, self.per_channel_widths = per_channel_offsets, per_channel_widths
@@ -713,7 +715,7 @@ def _bn_fn(m: nn.BatchNorm2d):
 
 def build_circuit(model: nn.Module, calib: torch.Tensor, n_bits: int = 5, rounding_threshold_bits: int = 6,
                   p_error: float = 0.01, range_margin: float = 0.0, rounding_method: str = "exact",
-                  per_channel_offsets: bool = True, per_channel_widths: bool = False) -> Circuit:
+                  per_channel_offsets: bool = True, per_channel_widths: Optional[bool] = None) -> Circuit:
     if rounding_method not in ("exact", "approximate"):
         raise ValueError("rounding_method must be 'exact' or 'approximate'")
     circ = CircuitBuilder(model, calib, n_bits, rounding_threshold_bits, p_error, range_margin, per_channel_offsets,

@@ -75,9 +75,12 @@ def test_per_channel_offsets_are_centred_and_robust():
     g = torch.Generator().manual_seed(0)
     calib = torch.randn(40, 24, 16, 16, generator=g)
     unseen = torch.randn(3, 24, 16, 16, generator=g).numpy()
-    per = C.build_circuit(model, calib, 5, 6, 0.01)
+    per = C.build_circuit(model, calib, 5, 6, 0.01, per_channel_widths=False)
     wide = C.build_circuit(model, calib, 5, 6, 0.01, per_channel_offsets=False)
-    assert per.pbs_count()["tlu"] == wide.pbs_count()["tlu"] and per.pbs_count()["bit"] < 0.97 * wide.pbs_count()["bit"]
+    both = C.build_circuit(model, calib, 5, 6, 0.01)                                  # default: per-channel offsets and widths
+    assert per.pbs_count()["tlu"] == wide.pbs_count()["tlu"] == both.pbs_count()["tlu"]
+    assert both.pbs_count()["bit"] < 0.95 * per.pbs_count()["bit"] < 0.95 * 0.97 * wide.pbs_count()["bit"]
+    assert all(op.chan_bits is None for op in per.ops if op.kind != "tlu" or True) and any(op.chan_bits is not None for op in both.lookups())
     vals = {}
     C.evaluate_clear(per, C.quantize_input(per, calib.numpy()), collect=vals)
     for op in per.ops:
@@ -87,14 +90,24 @@ def test_per_channel_offsets_are_centred_and_robust():
             assert (lo >= 0).all() and (hi >= 0).all()
             lsbs = max(0, op.acc_bits - 6)
             assert (np.abs(lo - hi) <= (1 << lsbs) // 2 + 2).all()          # centred up to the rounding half and integer division
-    tlu, bit, _ = P.pick_parameters(per.noise_spec())
-    nm = C.NoiseModel.from_params(tlu, bit, tlu.glwe_std)
-    q = C.quantize_input(per, unseen)
-    clear = C.evaluate_clear(per, q)
-    span = int(clear.max() - clear.min())
-    for seed in range(2):
-        noisy = C.evaluate_clear(per, q, noise=nm, rng=np.random.default_rng(seed))
-        assert np.abs(noisy - clear).max() < 0.2 * span
+    for circ in (per, both):
+        tlu, bit, _ = P.pick_parameters(circ.noise_spec())
+        nm = C.NoiseModel.from_params(tlu, bit, tlu.glwe_std)
+        q = C.quantize_input(circ, unseen)
+        clear = C.evaluate_clear(circ, q)
+        span = int(clear.max() - clear.min())
+        for seed in range(2):
+            noisy = C.evaluate_clear(circ, q, noise=nm, rng=np.random.default_rng(seed))
+            assert np.abs(noisy - clear).max() < 0.2 * span
+    # per-channel widths: every channel fits its own width with symmetric slack
+    vals = {}
+    C.evaluate_clear(both, C.quantize_input(both, calib.numpy()), collect=vals)
+    for op in both.lookups():
+        lin = next(o for o in both.ops if getattr(o, "dst", None) == op.src)
+        u = vals[op.src] + C.channel_offsets(lin.offset, vals[op.src].shape[1]).reshape(1, -1, 1, 1)
+        top = (1 << op.chan_widths()) - 1
+        assert (u.min(axis=(0, 2, 3)) >= 0).all() and (u.max(axis=(0, 2, 3)) <= top).all()
+        assert (op.chan_widths() <= op.acc_bits).all() and (op.chan_widths() >= min(op.acc_bits, 6)).all()
 
 
 def test_rounding_semantics_of_tlu_apply():

@@ -45,7 +45,8 @@ def _worker(rank, world, port, ret):
                 acc, lo, hi, per = acc_local.pop(op.src)
                 Cc, H, W = op.shape
                 lin = next(o for o in circ.ops if getattr(o, "dst", None) == op.src)
-                sub = C.TluOp(op.name, op.src, op.dst, (hi - lo, H, W), op.acc_bits, op.keep_bits, op.tables[lo:hi], op.out)
+                sub = C.TluOp(op.name, op.src, op.dst, (hi - lo, H, W), op.acc_bits, op.keep_bits, op.tables[lo:hi], op.out,
+                              chan_bits=None if op.chan_bits is None else op.chan_bits[lo:hi])
                 out = C.tlu_apply(sub, C.channel_offsets(lin.offset, Cc)[lo:hi], acc[None])[0] if hi > lo else np.zeros((0, H, W), np.int64)
                 local = torch.from_numpy(out.reshape(-1, 1).astype(np.int64))
                 full = gather_channels(local, Cc, per, H * W, world)
