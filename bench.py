@@ -269,6 +269,7 @@ def run_gpu(args):
             "dtype": "u64+f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "parallelism": f"layer-partitioned x{world}", "pbs_per_image": cnt["total"],
                        "pbs_tlu": cnt["tlu"], "pbs_bit": cnt["bit"], "conv_macs": circ.macs(),
+                       "accumulator_layout": "one centred offset and one width per channel (tfx_b200/circuit.py, DESIGN.md 3)",
                        "tlu_set": vars(tlu) if hasattr(tlu, "__dict__") else str(tlu), "bit_set": str(bit),
                        "l2": (f"no flush: every lookup layer streams its ciphertext tensor ({min(int(np.prod(op.shape)) for op in circ.lookups() if int(np.prod(op.shape)) > 64) * ex.words * 8 / 1e6:.0f}"
                               f"-{max(int(np.prod(op.shape)) for op in circ.lookups()) * ex.words * 8 / 1e6:.0f} MB) several times between two uses of any buffer, and the "
