@@ -18,7 +18,7 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 import torch
 
-from .binding import Context, KeySet, PbsParams, launch_count
+from .binding import Context, KeySet, PbsParams, TfxError, launch_count
 from .circuit import Circuit, ConvOp, AddOp, TluOp, channel_offsets
 
 MASK64 = (1 << 64) - 1
@@ -95,7 +95,12 @@ class CircuitExecutor:
                  rank: int = 0, world_size: int = 1, process_group=None, input_std: Optional[float] = None):
         self.circ = circuit
         self.params = list(params)
-        self.ctx = ctx if ctx is not None else Context(torch.cuda.current_device())
+        if ctx is None:
+            if not torch.cuda.is_available():
+                raise TfxError("CUDA device required: the TFHE execution path has no CPU fallback "
+                               "(fhe='disable' / 'simulate' run without a GPU; keygen() and fhe='execute' do not)")
+            ctx = Context(torch.cuda.current_device())
+        self.ctx = ctx
         self.rank, self.world = rank, world_size
         self.pg = process_group
         self.big_dim = max(p.big_dim for p in params)
