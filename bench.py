@@ -308,6 +308,50 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+
+# ------------------------------------------------------------------------------------------------------------
+# DCT preprocessing row: python bench.py --preprocess [--batch N]
+# ------------------------------------------------------------------------------------------------------------
+def run_preprocess(args):
+    """Throughput of the batched torch DCT pipeline on the GPU (CUDA events; images resident, and host to host from pinned
+    memory) with the numpy oracle — the per-image CPU restatement of the reference's transform — as cpu_baseline and checker.
+    Synthetic CIFAR-sized RGB images, the headline configuration (24 channels, 16x16, 4x4 blocks)."""
+    import torch
+    from tfx_b200.dct_preprocess import DctPreprocessor
+    rng = np.random.default_rng(0)
+    imgs = rng.integers(0, 256, size=(args.batch, 32, 32, 3), dtype=np.uint8)
+    dev = torch.device("cuda:0" if torch.cuda.is_available() else "cpu")
+    pre = DctPreprocessor(16, 4, 24, device=dev)
+    out = {"metric": "dct_preprocess_throughput", "unit": "images/s", "config": {"workload": "24 channels, 16x16, 4x4 block DCT, 32x32 RGB inputs",
+                                                                                 "batch": args.batch}, "device": str(dev), "data": "synthetic"}
+    if dev.type == "cuda":
+        host = torch.from_numpy(imgs).pin_memory()
+        x = host.to(dev)
+        for _ in range(3):
+            y = pre(x)
+        torch.cuda.synchronize()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        res = torch.empty(args.batch, 24, 16, 16, dtype=torch.float32).pin_memory()
+        e[0].record(); y = pre(x); e[1].record()
+        e[2].record(); y2 = pre(host.to(dev, non_blocking=True)); res.copy_(y2, non_blocking=True); e[3].record()
+        torch.cuda.synchronize()
+        out["value"] = args.batch / (e[0].elapsed_time(e[1]) / 1e3)
+        out["e2e"] = {"value": args.batch / (e[2].elapsed_time(e[3]) / 1e3), "unit": "images/s", "h2d_bytes_per_step": imgs.nbytes,
+                      "d2h_bytes_per_step": res.numel() * 4}
+        got = y[: args.cpu_images].cpu().numpy()
+    else:
+        t0 = time.time(); y = pre(imgs); dt = time.time() - t0
+        out["value"] = args.batch / dt
+        got = y[: args.cpu_images].numpy()
+    from oracle import dct_oracle as DO                        # cpu_baseline leg + checker
+    t0 = time.time()
+    ref = np.stack([DO.preprocess(imgs[i], 16, 4, 24) for i in range(args.cpu_images)])
+    out["cpu_baseline"] = {"value": args.cpu_images / (time.time() - t0), "unit": "images/s", "cores": 1, "kind": "port",
+                           "sample": f"{args.cpu_images} images through oracle/dct_oracle.py (numpy restatement of the reference's per-image transform)"}
+    tol = 2 * np.spacing(np.maximum(np.abs(ref), np.float32(1e-3)))
+    out["check"] = {"values_beyond_2_ulp": int((np.abs(got - ref) > tol).sum()), "compared": int(ref.size)}
+    print(json.dumps(out), flush=True)
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -316,8 +360,13 @@ def main():
     ap.add_argument("--impl", default="tfx", choices=["tfx", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=256, help="ciphertexts per CPU sample step (about 10 s of host work on 16 threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--preprocess", action="store_true", help="measure the DCT preprocessing row instead of the encrypted circuit")
+    ap.add_argument("--batch", type=int, default=4096, help="--preprocess: images per batch")
+    ap.add_argument("--cpu-images", type=int, default=64, help="--preprocess: images through the CPU oracle")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.preprocess:
+        run_preprocess(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)
