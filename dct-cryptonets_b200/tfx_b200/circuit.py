@@ -15,6 +15,7 @@ below and the CPU oracle's evaluator (oracle/circuit_oracle.py, test infrastruct
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional, Tuple
 
@@ -398,8 +399,8 @@ class CircuitBuilder:
                  p_error: float = 0.01, range_margin: float = 0.0, per_channel_offsets: bool = True,
                  per_channel_widths: Optional[bool] = None):
         self.model = model.eval()
-        if per_channel_widths is None:
-            per_channel_widths = per_channel_offsets
+        if per_channel_widths is None:                       # default on; TFX_PER_CHANNEL_WIDTHS=0 switches it off for A/B measurements
+            per_channel_widths = per_channel_offsets and os.environ.get("TFX_PER_CHANNEL_WIDTHS", "1") != "0"
         if per_channel_widths and not per_channel_offsets:
             raise ValueError("per_channel_widths needs per_channel_offsets")
         self.per_channel_offsets, self.per_channel_widths = per_channel_offsets, per_channel_widths
