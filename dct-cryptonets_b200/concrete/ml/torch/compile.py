@@ -32,7 +32,7 @@ def compile_torch_model(torch_model: torch.nn.Module, torch_inputset, n_bits: Un
         torch_inputset = torch.from_numpy(torch_inputset)
     bits, method = _rounding(rounding_threshold_bits)
     # backend-specific options (not part of Concrete-ML's signature): accumulator layout, see tfx_b200/circuit.py
-    layout = {k: kwargs[k] for k in ("per_channel_offsets", "per_channel_widths") if k in kwargs}
+    layout = {k: kwargs[k] for k in ("per_channel_offsets", "per_channel_widths", "fuse_residual") if k in kwargs}
     return QuantizedModule.compile(torch_model, torch_inputset, n_bits=int(n_bits),
                                    rounding_threshold_bits=bits, rounding_method=method,
                                    p_error=0.01 if p_error is None else float(p_error), configuration=configuration,

@@ -73,6 +73,25 @@ class AddOp:
 
 
 @dataclass
+class FusedAddOp:
+    """dst = a + m_c * b (fuse_residual, opt-in): `a` is the accumulator of a conv whose float chain is affine per channel (BatchNorm),
+    `b` a quantised tensor (the identity shortcut).  real(a-chain) + real(b) = g_c * (a + r_c * b) + beta_c with r_c = s_b / g_c; the
+    integer m_c = round(r_c) stands in for r_c (|r_c| >= 8, so the shortcut's weight is off by < 1/16 and typically ~1 %), and
+    the block needs one table lookup instead of two.  The conv is emitted at this op's width (same encoding), so the sum is leveled."""
+    name: str
+    a: int                      # conv accumulator (value id)
+    b: int                      # quantised tensor (value id)
+    dst: int
+    shape: Tuple[int, int, int]
+    m: np.ndarray               # int64 [C]
+    acc_bits: int = 0
+    offset: object = 0          # int64 [C]
+    sb: Optional[np.ndarray] = None   # int64 [C]: m_c * 2^(emitted width of b - acc_bits), set when widths are final
+    chan_bits: Optional[np.ndarray] = None
+    kind: str = "fadd"
+
+
+@dataclass
 class TluOp:
     name: str
     src: int                    # accumulator value (output of a conv / add)
@@ -139,7 +158,7 @@ class Circuit:
         return total
 
     def maximum_integer_bit_width(self) -> int:
-        widths = [op.acc_bits for op in self.ops if op.kind in ("conv", "add")]
+        widths = [op.acc_bits for op in self.ops if op.kind in ("conv", "add", "fadd")]
         return max(widths + [self.input_width])
 
     def noise_spec(self, input_std: float = 2.0 ** -50) -> CircuitNoiseSpec:
@@ -151,6 +170,10 @@ class Circuit:
                 w = lin.weight.astype(np.float64)
                 norm2 = float((w.reshape(w.shape[0], -1) ** 2).sum(axis=1).max())
                 fresh = lin.src == self.input_id
+            elif lin.kind == "fadd":
+                w = producers[lin.a].weight.astype(np.float64)
+                norm2 = float((w.reshape(w.shape[0], -1) ** 2).sum(axis=1).max()) + float((np.asarray(lin.sb, dtype=np.float64) ** 2).max())
+                fresh = False
             else:
                 norm2 = float(lin.sa ** 2 + lin.sb ** 2)
                 fresh = False
@@ -172,6 +195,9 @@ class Circuit:
                 k = "sum_pool" if op.depthwise else "conv2d"
                 lines.append(f"  %{op.dst} = {k}(%{op.src}) {{weight=i32{list(op.weight.shape)}, stride={op.stride}, pad={op.pad}, "
                              f"lshift={op.lshift}, offset={_offset_text(op.offset)}}} : eint<{op.acc_bits}>{list(op.out_shape)}   // {op.name}")
+            elif op.kind == "fadd":
+                lines.append(f"  %{op.dst} = fused_add(%{op.a}, %{op.b} * [{int(np.min(op.sb))}..{int(np.max(op.sb))}]/channel) "
+                             f"{{offset={_offset_text(op.offset)}}} : eint<{op.acc_bits}>{list(op.shape)}   // {op.name}")
             elif op.kind == "add":
                 lines.append(f"  %{op.dst} = add(%{op.a} * {op.sa}, %{op.b} * {op.sb}) {{offset={_offset_text(op.offset)}}} : eint<{op.acc_bits}>{list(op.shape)}   // {op.name}")
             else:
@@ -299,6 +325,9 @@ def evaluate_clear(circ: Circuit, q_in: np.ndarray, collect: Optional[dict] = No
         elif op.kind == "add":
             vals[op.dst] = vals[op.a] + vals[op.b]
             offs[op.dst] = op.offset
+        elif op.kind == "fadd":
+            vals[op.dst] = vals[op.a] + _chan_view(op.m) * vals[op.b]
+            offs[op.dst] = op.offset
         elif noise is None:
             vals[op.dst] = tlu_apply(op, offs[op.src], vals[op.src])
         else:
@@ -397,8 +426,10 @@ def _fake_quant_fn(q: QuantInfo):
 class CircuitBuilder:
     def __init__(self, model: nn.Module, calib: torch.Tensor, n_bits: int = 5, rounding_threshold_bits: int = 6,
                  p_error: float = 0.01, range_margin: float = 0.0, per_channel_offsets: bool = True,
-                 per_channel_widths: Optional[bool] = None):
+                 per_channel_widths: Optional[bool] = None, fuse_residual: bool = False):
         self.model = model.eval()
+        # opt-in (TFX_FUSE_RESIDUAL=1 for A/B runs): validated against the oracle on the CPU only, never run on a GPU yet
+        self.fuse_residual = fuse_residual or os.environ.get("TFX_FUSE_RESIDUAL", "0") == "1"
         if per_channel_widths is None:                       # default on; TFX_PER_CHANNEL_WIDTHS=0 switches it off for A/B measurements
             per_channel_widths = per_channel_offsets and os.environ.get("TFX_PER_CHANNEL_WIDTHS", "1") != "0"
         if per_channel_widths and not per_channel_offsets:
@@ -644,7 +675,44 @@ class CircuitBuilder:
         f = 1.0 / (k * k)
         return _Sym(vid, True, self.qinfo[q].scale, [lambda y, f=f: y * f], op.out_shape, True, f)
 
+    def _try_fused_add(self, node, a: _Sym, b: _Sym, ka, kb) -> Optional[_Sym]:
+        """a: unmaterialised conv accumulator with a per-channel affine chain (BatchNorm); b: quantised tensor.  See FusedAddOp."""
+        qb = self.materialized.get(kb) if b.lin_is_acc else (b.lin if not b.chain else None)   # b must already exist as a quantised tensor
+        if not (a.lin_is_acc and a.chain and ka not in self.materialized and qb is not None):
+            return None
+        conv = self.acc_of.get(a.lin)
+        if conv is None or conv.kind != "conv" or conv.depthwise:
+            return None
+        C = self.ints[a.lin].shape[1]
+        probe = torch.tensor([0.0, 1.0, 1024.0], dtype=torch.float64).reshape(1, 1, 3, 1).expand(1, C, 3, 1) * a.scale
+        y = probe
+        for fn in a.chain:
+            y = fn(y)
+        y = y.reshape(C, 3).numpy()
+        g = y[:, 1] - y[:, 0]                                              # real value per accumulator unit, per channel
+        if not np.allclose(y[:, 2], y[:, 0] + 1024.0 * g, rtol=1e-9, atol=1e-12) or not np.all(np.isfinite(g)) or np.any(g == 0):
+            return None                                                    # chain is not affine
+        r = self.qinfo[qb].scale / g
+        if np.abs(r).min() < 8.0 or np.abs(r).max() > 4096.0:
+            return None
+        m = np.rint(r).astype(np.int64)
+        vid = self._new()
+        op = FusedAddOp(f"fadd_{node.name}", a.lin, qb, vid, tuple(self.ints[a.lin].shape[1:]), m)
+        acc = self.ints[a.lin] + m.reshape(1, C, 1, 1) * self.ints[qb]
+        self._finish_acc(op, acc)
+        # the conv is emitted directly at the fused accumulator's encoding: no table lookup reads it, no offset of its own
+        conv.acc_bits, conv.offset, conv.chan_bits = op.acc_bits, np.zeros(C, dtype=np.int64), None
+        self.ops.append(op)
+        self.ints[vid] = acc
+        self.acc_of[vid] = op
+        self._register(qb, op, "b")
+        return _Sym(vid, True, a.scale, list(a.chain), op.shape)
+
     def _add(self, node, a: _Sym, b: _Sym, ka, kb) -> _Sym:
+        if self.fuse_residual:
+            fused = self._try_fused_add(node, a, b, ka, kb) or self._try_fused_add(node, b, a, kb, ka)
+            if fused is not None:
+                return fused
         # operands must share one scale: an already-quantised operand dictates it, otherwise the larger range does
         qa = self.materialized.get(ka) if a.lin_is_acc else a.lin
         qb = self.materialized.get(kb) if b.lin_is_acc else b.lin
@@ -690,6 +758,8 @@ class CircuitBuilder:
                 if op.kind == "conv":
                     op.lshift = ls
                     op.weight = (op.raw_weight.astype(np.int64) << ls).astype(np.int32)
+                elif op.kind == "fadd":
+                    op.sb = op.m << ls
                 elif role == "a":
                     op.sa = 1 << ls
                 else:
@@ -716,10 +786,11 @@ def _bn_fn(m: nn.BatchNorm2d):
 
 def build_circuit(model: nn.Module, calib: torch.Tensor, n_bits: int = 5, rounding_threshold_bits: int = 6,
                   p_error: float = 0.01, range_margin: float = 0.0, rounding_method: str = "exact",
-                  per_channel_offsets: bool = True, per_channel_widths: Optional[bool] = None) -> Circuit:
+                  per_channel_offsets: bool = True, per_channel_widths: Optional[bool] = None,
+                  fuse_residual: bool = False) -> Circuit:
     if rounding_method not in ("exact", "approximate"):
         raise ValueError("rounding_method must be 'exact' or 'approximate'")
     circ = CircuitBuilder(model, calib, n_bits, rounding_threshold_bits, p_error, range_margin, per_channel_offsets,
-                          per_channel_widths).build()
+                          per_channel_widths, fuse_residual).build()
     circ.rounding_method = rounding_method
     return circ

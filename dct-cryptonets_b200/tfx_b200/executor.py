@@ -242,7 +242,7 @@ class CircuitExecutor:
         # liveness: a layer tensor (hundreds of MB to GB) is released after its last consumer
         last_use: Dict[int, int] = {}
         for i, op in enumerate(circ.ops):
-            for src in ((op.src,) if op.kind != "add" else (op.a, op.b)):
+            for src in ((op.a, op.b) if op.kind in ("add", "fadd") else (op.src,)):
                 last_use[src] = i
         last_use[circ.output_id] = len(circ.ops)
         for i, op in enumerate(circ.ops):
@@ -274,6 +274,20 @@ class CircuitExecutor:
                         acc = torch.empty_like(a)
                         for c in range(hi - lo):
                             timed("add", H * W, lambda: ctx.axpby(a[c], op.sa, b[c], op.sb, body_const=int(consts[lo + c]), out=acc[c]))
+                else:
+                    acc = ctx.empty_u64(0, H, W, words)
+                acc_local[op.dst] = (acc.view(-1, words), lo, hi, per)
+            elif op.kind == "fadd":
+                # fused residual add (opt-in, circuit.FusedAddOp): this rank's conv accumulators + m_c * shortcut, per channel
+                conv_acc, lo, hi, per = acc_local.pop(op.a)
+                C, H, W = op.shape
+                consts = self._body_constants(op, C)
+                if hi > lo:
+                    a = conv_acc.view(hi - lo, H, W, words)
+                    b = vals[op.b][lo:hi].contiguous()
+                    acc = torch.empty_like(a)
+                    for c in range(hi - lo):
+                        timed("add", H * W, lambda: ctx.axpby(a[c], 1, b[c], int(op.sb[lo + c]), body_const=int(consts[lo + c]), out=acc[c]))
                 else:
                     acc = ctx.empty_u64(0, H, W, words)
                 acc_local[op.dst] = (acc.view(-1, words), lo, hi, per)

@@ -91,11 +91,12 @@ class QuantizedModule:
     @classmethod
     def compile(cls, torch_model, inputset: torch.Tensor, n_bits: int, rounding_threshold_bits: int, p_error: float,
                 configuration=None, verbose: bool = False, params=None, rounding_method: str = "exact",
-                per_channel_offsets: bool = True, per_channel_widths: Optional[bool] = None) -> "QuantizedModule":
+                per_channel_offsets: bool = True, per_channel_widths: Optional[bool] = None,
+                fuse_residual: bool = False) -> "QuantizedModule":
         t0 = time.time()
         circ = C.build_circuit(torch_model, inputset, n_bits=n_bits, rounding_threshold_bits=rounding_threshold_bits, p_error=p_error,
                                rounding_method=rounding_method, per_channel_offsets=per_channel_offsets,
-                               per_channel_widths=per_channel_widths)
+                               per_channel_widths=per_channel_widths, fuse_residual=fuse_residual)
         if params is None:
             tlu, bit, info = pick_parameters(circ.noise_spec())
         else:

@@ -102,6 +102,11 @@ def run_circuit(circ, keys: OracleKeys, in_cts: np.ndarray, collect: Optional[Di
             t0 = time.time()
             vals[op.dst] = O.conv2d(vals[op.src], op.weight, op.stride, op.pad, bias, depthwise=op.depthwise)
             t_lin += time.time() - t0
+        elif op.kind == "fadd":
+            consts = _body_constants(op.offset, lsbs_after.get(op.dst), op.acc_bits, op.shape[0])
+            t0 = time.time()
+            vals[op.dst] = np.stack([O.axpby(vals[op.a][c], 1, vals[op.b][c], int(op.sb[c]), int(consts[c])) for c in range(op.shape[0])])
+            t_lin += time.time() - t0
         elif op.kind == "add":
             consts = _body_constants(op.offset, lsbs_after.get(op.dst), op.acc_bits, op.shape[0])
             t0 = time.time()

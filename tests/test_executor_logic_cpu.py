@@ -80,24 +80,26 @@ class FakeKeys:
         return _pt(r)
 
 
-def _net():
+def _net(spread: bool = True):
     torch.manual_seed(4)
     net = nn.Sequential(nn.Conv2d(3, 5, 1, bias=False), nn.BatchNorm2d(5), nn.ReLU(), ResidualBlock(5, 5, False),
                         ResidualBlock(5, 7, True), nn.AvgPool2d(2), nn.Flatten()).eval()
     for m in net.modules():                                  # uneven channel ranges so that per-channel widths really differ
         if isinstance(m, nn.BatchNorm2d):
-            m.weight.data = torch.linspace(0.2, 2.0, m.num_features)
+            m.weight.data = torch.linspace(0.2, 2.0, m.num_features) if spread else torch.linspace(0.1, 0.2, m.num_features)
             m.bias.data = torch.linspace(-0.5, 0.5, m.num_features)
     return net, torch.randn(32, 3, 4, 4)
 
 
-@pytest.mark.parametrize("mode", ["tensor_wide", "per_channel_offsets", "per_channel_widths", "approximate_widths"])
+@pytest.mark.parametrize("mode", ["tensor_wide", "per_channel_offsets", "per_channel_widths", "approximate_widths", "fused_widths"])
 def test_executor_host_logic_equals_oracle_circuit(oracle, mode):
     from oracle import circuit_oracle as CO
-    net, calib = _net()
+    net, calib = _net(spread=not mode.startswith("fused"))      # small BatchNorm gains: the shortcut's integer weight m_c is >= 8
     circ = C.build_circuit(net, calib, n_bits=5, rounding_threshold_bits=6, p_error=0.01,
                            per_channel_offsets=(mode != "tensor_wide"), per_channel_widths=mode.endswith("widths"),
-                           rounding_method="approximate" if mode.startswith("approximate") else "exact")
+                           rounding_method="approximate" if mode.startswith("approximate") else "exact",
+                           fuse_residual=mode.startswith("fused"))
+    assert any(op.kind == "fadd" for op in circ.ops) == mode.startswith("fused")
     if mode.endswith("widths"):
         assert any(op.chan_bits is not None and len(set(op.chan_bits.tolist())) > 1 for op in circ.lookups())
     okeys = CO.OracleKeys((TLU, BIT), 9)
