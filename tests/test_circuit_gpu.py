@@ -210,29 +210,3 @@ def test_approximate_rounding_matches_oracle_and_clear(gpu_ctx, oracle):
     # approximate rounding: the mod-switch noise blurs every rounding threshold (that is the approximation), so the
     # decrypted features track the clear evaluation without being equal to it
     assert np.abs(dec - clear).max() <= 0.35 * max(1.0, np.abs(clear).max()), (dec, clear)
-
-
-@pytest.mark.xfail(strict=False, reason="fuse_residual is opt-in and was validated against the oracle on the CPU only "
-                                        "(tests/test_executor_logic_cpu.py[fused_widths]); first GPU run pending")
-def test_fused_residual_lookups_match_oracle_and_clear(gpu_ctx, oracle):
-    """opt-in fused residual lookups (circuit.FusedAddOp): GPU ciphertexts == oracle circuit word for word, decrypted == clear"""
-    from oracle import circuit_oracle as CO
-    torch.manual_seed(4)
-    net = nn.Sequential(nn.Conv2d(3, 5, 1, bias=False), nn.BatchNorm2d(5), nn.ReLU(), ResidualBlock(5, 5, False),
-                        ResidualBlock(5, 7, True), nn.AvgPool2d(2), nn.Flatten()).eval()
-    for m in net.modules():
-        if isinstance(m, nn.BatchNorm2d):
-            m.weight.data = torch.linspace(0.1, 0.2, m.num_features)
-            m.bias.data = torch.linspace(-0.5, 0.5, m.num_features)
-    calib = torch.randn(32, 3, 4, 4)
-    circ = C.build_circuit(net, calib, n_bits=5, rounding_threshold_bits=6, p_error=0.01, fuse_residual=True)
-    assert any(op.kind == "fadd" for op in circ.ops)
-    ex = CircuitExecutor(circ, (TOY_TLU, TOY_BIT), ctx=gpu_ctx, input_std=2.0**-50)
-    ex.keygen(seed=15)
-    q_in = C.quantize_input(circ, calib[:1].numpy())[0]
-    got = gpu_ctx.to_host_u64(ex.run(ex.encrypt(q_in, enc_seed=16)))
-    keys = CO.OracleKeys((TOY_TLU, TOY_BIT), 15)
-    ref = CO.run_circuit(circ, keys, CO.encrypt_input(circ, keys, q_in, 2.0**-50, 16))
-    assert np.array_equal(got, ref)
-    clear = C.evaluate_clear(circ, q_in[None])[0]
-    assert np.array_equal(CO.decrypt_output(circ, keys, ref).reshape(clear.shape), clear)
