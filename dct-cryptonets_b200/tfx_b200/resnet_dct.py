@@ -3,7 +3,7 @@
 Own restatement of the topology defined by the reference at models/backbone.py:18-58 (SimpleBlock),
 :107-184 (ResNetDCT), :291-342 (factories) and the stem table :347-582 — the part of the reference that defines
 the work of the encrypted path (which convs, where the table lookups sit).  It exists because /root/reference is
-not present on the GPU box; tests/test_topology_vs_reference.py checks it against the reference modules in the
+not present on the GPU box; tests/test_circuit_cpu.py::test_topology_matches_reference_modules checks it against the reference modules in the
 build container.  Attribute names (.trunk, .final_feat_dim, C1/BN1/relu1/C2/BN2/relu2/shortcut/BNshortcut)
 follow the reference so the same compile front-end accepts either.
 """
