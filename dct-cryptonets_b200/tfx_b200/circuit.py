@@ -370,6 +370,11 @@ class _Sym:
     pending_input: bool = False               # the raw float input, not quantised yet (its first consumer decides how)
 
 
+# head-room (fraction of its span, per side) kept by a channel that is narrower than its tensor; 1/16 brings the rate of
+# out-of-range accumulators on unseen inputs back to what tensor-wide calibration gives
+NARROW_SLACK = float(os.environ.get("TFX_NARROW_SLACK", "0.0625"))
+
+
 def _bits_for_range(lo: int, hi: int) -> int:
     span = hi - lo + 1
     return max(1, int(math.ceil(math.log2(span)))) if span > 1 else 1
@@ -474,7 +479,10 @@ class CircuitBuilder:
         op.acc_bits = w
         if self.per_channel_offsets:
             if self.per_channel_widths and w > self.t:
-                w_c = np.array([min(w, max(self.t, width_for(int(sp)))) for sp in span_c], dtype=np.int64)
+                # a channel narrower than the tensor keeps NARROW_SLACK of its span as head-room on each side (the widest
+                # channels, which set the tensor's width, keep what tensor-wide calibration gives them)
+                w_c = np.array([min(w, max(self.t, width_for(int(math.ceil(sp * (1.0 + 2.0 * NARROW_SLACK))))))
+                                for sp in span_c], dtype=np.int64)
                 if (w_c < w).any():
                     op.chan_bits = w_c
             else:
