@@ -26,23 +26,38 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "dct-cryptonets_b200"))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = "DCT-ResNet-20, one synthetic 24x16x16 DCT-domain image, n_bits=5, rounding_threshold_bits=6, p_error=0.01"
 METRIC = "encrypted_image_latency"
 UNIT = "s/image"
+# BASELINE.json configs (configs[1], the kernel sweep, is tools/microbench.py).  Deviations from the reference's stem
+# tables for 3 and 4 are SURVEY.md 3.4's; 5 runs one image per GPU (replicas only).
+CONFIGS = {
+    1: ("DCT-ResNet-20, one synthetic 24x16x16 DCT-domain image, n_bits=5, rounding_threshold_bits=6, p_error=0.01",
+        lambda R: R.resnet20_dct(24, 16), (24, 16, 16), 6),
+    3: ("ResNet-20 on raw RGB, one synthetic 3x32x32 image (skip_single_downsample=False), n_bits=5, rounding_threshold_bits=6, p_error=0.01",
+        lambda R: R.resnet20_dct(3, 32, skip_single_downsample=False), (3, 32, 32), 6),
+    4: ("DCT-ResNet-18, one synthetic 24x16x16 DCT-domain image (stem key '64_24_16'), n_bits=5, rounding_threshold_bits=6, p_error=0.01",
+        lambda R: R.resnet18_dct(24, 16), (24, 16, 16), 6),
+    5: ("DCT-ResNet-18, ImageNette-size 64x56x56 DCT-domain input, one synthetic image per GPU (replicas), n_bits=5, "
+        "rounding_threshold_bits=6, p_error=0.01",
+        lambda R: R.resnet18_dct(64, 56), (64, 56, 56), 6),
+}
+WORKLOAD = CONFIGS[1][0]
 
 
-def build_circuit_and_params():
+def build_circuit_and_params(config: int = 1, image_seed: int = 0):
     import torch
-    from tfx_b200 import circuit as C, params as P
-    from tfx_b200.resnet_dct import resnet20_dct
+    from tfx_b200 import circuit as C, params as P, resnet_dct as R
+    workload, make, shape, t_bits = CONFIGS[config]
     torch.manual_seed(0)
-    model = resnet20_dct(24, 16).eval()
+    model = make(R).eval()
     g = torch.Generator().manual_seed(0)
-    calib = torch.randn(100, 24, 16, 16, generator=g)
-    circ = C.build_circuit(model, calib, n_bits=5, rounding_threshold_bits=6, p_error=0.01)
+    calib = torch.randn(100, *shape, generator=g)
+    circ = C.build_circuit(model, calib, n_bits=5, rounding_threshold_bits=t_bits, p_error=0.01)
     tlu, bit, info = P.pick_parameters(circ.noise_spec())
-    image = torch.randn(1, 24, 16, 16, generator=g).numpy()
-    return circ, (tlu, bit), info, image
+    image = torch.randn(1, *shape, generator=g).numpy()
+    if image_seed:                                       # replicas: every rank its own image
+        image = torch.randn(1, *shape, generator=torch.Generator().manual_seed(1000 + image_seed)).numpy()
+    return model, circ, (tlu, bit), info, image
 
 
 def peaks():
@@ -107,6 +122,8 @@ def cpu_sample(circ, params, sample_cts: int = 32):
     global _ORACLE_KEYS
     from oracle import oracle as O, circuit_oracle as CO
     O.build()
+    # all the host cores this process may use, set explicitly: torchrun exports OMP_NUM_THREADS=1 for nproc-per-node > 1
+    O.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     tlu, bit = params
     if _ORACLE_KEYS is None:
         _ORACLE_KEYS = CO.OracleKeys(params, 1)
@@ -133,15 +150,25 @@ def cpu_sample(circ, params, sample_cts: int = 32):
 
 
 def run_reference(args):
+    """CPU arm: the oracle port on every host core, one bounded sample per step.  Under torchrun only rank 0 works."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    circ, params, info, image = build_circuit_and_params()
+    t_start = time.time()
+    _, circ, params, info, image = build_circuit_and_params(args.config)
+    # size the per-step sample so that warmup + steps samples end within about two minutes on this host
+    _, _, threads = cpu_sample(circ, params, sample_cts=8)                # also builds the oracle keys (untimed)
+    t0 = time.time()
+    cpu_sample(circ, params, sample_cts=max(8, threads))
+    per_ct = (time.time() - t0) / max(8, threads)
+    budget = 100.0 / max(1, args.warmup + args.steps)
+    sample = int(min(args.cpu_sample, max(threads, budget / max(per_ct, 1e-6))))
+    sample = max(threads, sample - sample % max(1, threads))
     lat = []
-    desc, threads = "", 1
+    desc = ""
     for it in range(args.warmup + args.steps):
         t0 = time.time()
-        v, desc, threads = cpu_sample(circ, params, sample_cts=args.cpu_sample)
+        v, desc, threads = cpu_sample(circ, params, sample_cts=sample)
         if it >= args.warmup:
             lat.append((v, time.time() - t0))
     value = statistics.mean(v for v, _ in lat)
@@ -149,13 +176,16 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": statistics.mean(w for _, w in lat) * 1e3, "higher_is_better": False,
-        "scaling": "strong", "vs_baseline": None, "dtype": "u64+f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "pbs_per_image": cnt["total"], "note": "value is extrapolated from the bounded sample"},
+        "scaling": "weak" if args.config == 5 else "strong", "vs_baseline": None, "dtype": "u64+f64", "data": "synthetic",
+        "config": {"workload": CONFIGS[args.config][0], "pbs_per_image": cnt["total"],
+                   "note": "value is extrapolated from the bounded sample of each step; host cores only, no GPU",
+                   "host_cores": threads, "wall_s": None},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "pbs_per_sec": cnt["total"] / value,
         "published_context": "reference README.md:84 reports 565 s on 96 CPU cores with Concrete (not runnable here; parity unpinned)",
     }
+    line["config"]["wall_s"] = time.time() - t_start
     print(json.dumps(line), flush=True)
 
 
@@ -163,11 +193,12 @@ def run_reference(args):
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------
 def run_gpu(args):
+    import hashlib
     import torch
     import torch.distributed as dist
-    from tfx_b200 import params as P
+    from tfx_b200 import circuit as C, params as P
     from tfx_b200.binding import Context, launch_count
-    from tfx_b200.executor import CircuitExecutor, RunStats
+    from tfx_b200.quantized_module import FheCircuit, QuantizedModule
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -180,36 +211,34 @@ def run_gpu(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         pg = dist.group.WORLD
+    replicas = args.config == 5 and world > 1            # one image per GPU, no data-path collective
 
-    circ, params, info, image = build_circuit_and_params()
+    model, circ, params, info, image = build_circuit_and_params(args.config, image_seed=rank if replicas else 0)
     tlu, bit = params
-    ctx = Context(local)
-    ex = CircuitExecutor(circ, params, ctx=ctx, rank=rank, world_size=world, process_group=pg)
-    t_keygen = ex.keygen(seed=1)
-    from tfx_b200 import circuit as C
-    q_in = C.quantize_input(circ, image)[0]
-    cts_dev = ex.encrypt(q_in, enc_seed=2)
-    host_in = torch.empty(cts_dev.shape, dtype=cts_dev.dtype, pin_memory=True)
-    host_in.copy_(cts_dev)
-    n_out = int(np.prod(circ.output_shape))
-    host_out = torch.empty((n_out, ex.words), dtype=cts_dev.dtype, pin_memory=True)
+    # the reference-facing object: q_module.forward(numpy, fhe='execute') -> numpy (homomorphic_eval.py:70)
+    qm = QuantizedModule(FheCircuit(circ, params, info), model)
+    fc = qm.fhe_circuit
+    if world > 1 and not replicas:
+        fc.configure_distributed(rank, world, pg)
+    fc.profile_kernels = True
+    t0 = time.time()
+    fc.keygen(seed=1, encryption_seed=2)                 # fixed seeds: every N reproduces the same ciphertext words (output_sha)
     torch.cuda.synchronize()
+    t_keygen = time.time() - t0
+    ex = fc.executor
+    ctx = ex.ctx
+    q_in = C.quantize_input(circ, image)[0]
+    n_in, n_out = int(q_in.size), int(np.prod(circ.output_shape))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(stats=None, profile=False):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        ev[0].record()
-        cts_dev.copy_(host_in, non_blocking=True)
-        ev[1].record()
-        out = ex.run(cts_dev, stats, profile_kernels=profile)
-        ev[2].record()
-        host_out.copy_(out, non_blocking=True)
-        ev[3].record()
-        return ev
+    def step():
+        t0 = time.perf_counter()
+        y = qm.forward(image, fhe="execute")             # quantise, H2D, encrypt, run, decrypt, D2H, de-quantise
+        return time.perf_counter() - t0, fc.last_run_events, fc.last_run_stats, y
 
     for _ in range(args.warmup):
         step()
@@ -218,36 +247,39 @@ def run_gpu(args):
     if rank == 0:
         sampler.start()
     launches0 = launch_count()
-    stats = RunStats()
     t0 = time.time()
-    evs = [step(stats, profile=True) for _ in range(args.steps)]
+    res = [step() for _ in range(args.steps)]
     barrier()
     wall = time.time() - t0
     launches = launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    dev_s = sum(e[1].elapsed_time(e[2]) for e in evs) / 1e3 / args.steps
-    e2e_s = sum(e[0].elapsed_time(e[3]) for e in evs) / 1e3 / args.steps
+    dev_s = sum(e0.elapsed_time(e1) for _, (e0, e1), _, _ in res) / 1e3 / args.steps
+    e2e_s = sum(w for w, _, _, _ in res) / args.steps
     t = torch.tensor([wall / args.steps, dev_s, e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     step_s, dev_s, e2e_s = [float(v) for v in t.cpu()]
 
-    # correctness guard inside the bench: decrypted outputs must be in the clear evaluator's neighbourhood
-    dec = ex.decrypt(host_out.to(ctx.device))
+    # correctness guard inside the bench: decrypted outputs must be in the clear evaluator's neighbourhood, and the hash of
+    # the output ciphertext words must be the same at every N (same keys, same input ciphertexts, same circuit)
+    out_words = ctx.to_host_u64(fc.last_output)
+    output_sha = hashlib.sha256(out_words.tobytes()).hexdigest()[:16]
+    dec = ex.decrypt(fc.last_output)
     clear = C.evaluate_clear(circ, q_in[None])[0].reshape(-1)
     span = max(1, int(clear.max() - clear.min()))
     max_dev = int(np.abs(dec - clear).max())
 
     if rank == 0:
         cnt = circ.pbs_count()
-        ks = stats.kernel_seconds()                      # class -> (seconds, launches, units) over the timed steps, this rank
+        ks: dict = {}
+        for _, _, st, _ in res:                          # class -> (seconds, launches, units) over the timed steps, this rank
+            for k_, (s_, n_, u_) in st.kernel_seconds().items():
+                a_ = ks.get(k_, (0.0, 0, 0))
+                ks[k_] = (a_[0] + s_, a_[1] + n_, a_[2] + u_)
         hbm_peak, peak_src = peaks()
         dfma = ctx.probe_rate(0)
         imac = ctx.probe_rate(1)
         dom = max(("pbs_bit", "pbs_tlu"), key=lambda k: ks.get(k, (0, 0, 0))[0])
-        dom_p = bit if dom == "pbs_bit" else tlu
-        sec, nl, units = ks[dom]
-        flops = units * P.pbs_flops(dom_p)
         prof = {}
         ppath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(ppath):
@@ -260,44 +292,49 @@ def run_gpu(args):
                 return None
             f_ = u_ * P.pbs_flops(p_)
             return {"kernel": f"pbs_kernel<log2N={p_.N.bit_length() - 1},k={p_.k}> ({cls})", "bound": "fp64", "achieved": f_ / s_ / 1e12,
-                    "peak": dfma / 1e12, "unit": "TFLOP/s", "frac": f_ / s_ / dfma, "pbs_per_launch": u_ / n_, "avg_launch_ms": s_ / n_ * 1e3,
+                    "peak": dfma / 1e12, "unit": "TFLOP/s", "frac": f_ / s_ / dfma,
+                    "peak_source": "DFMA rate measured live by tfx_probe_rate (MEASURED_PEAKS.json has no FP64 figure)",
+                    "flops_per_pbs": P.pbs_flops(p_), "pbs_per_launch": u_ / n_, "avg_launch_ms": s_ / n_ * 1e3,
                     "share_of_step": s_ / total_kernel_s, "pbs_per_s": u_ / s_,
-                    "traffic": (prof.get(cls, {}).get("dram_bytes_per_unit") or 0) * u_ / n_ or None}
+                    "traffic": (prof.get(cls, {}).get("dram_bytes_per_unit") or 0) * u_ / n_ or None,
+                    "traffic_source": prof.get("source"),
+                    "hbm": {"achieved": n_ * P.bsk_bytes(p_) / s_ / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": n_ * P.bsk_bytes(p_) / s_ / 1e9 / hbm_peak, "peak_source": peak_src,
+                            "note": "algorithmic bootstrapping-key bytes per launch (one pass over the key serves the whole batch)"}}
+        sizes = [int(np.prod(op.shape)) for op in circ.lookups()]
         line = {
             "metric": METRIC, "value": dev_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": step_s * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": step_s * 1e3, "higher_is_better": False, "scaling": "weak" if replicas else "strong", "vs_baseline": None,
             "dtype": "u64+f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "parallelism": f"layer-partitioned x{world}", "pbs_per_image": cnt["total"],
-                       "pbs_tlu": cnt["tlu"], "pbs_bit": cnt["bit"], "conv_macs": circ.macs(),
-                       "accumulator_layout": "one centred offset and one width per channel (tfx_b200/circuit.py, DESIGN.md 3)",
-                       "tlu_set": vars(tlu) if hasattr(tlu, "__dict__") else str(tlu), "bit_set": str(bit),
-                       "l2": (f"no flush: every lookup layer streams its ciphertext tensor ({min(int(np.prod(op.shape)) for op in circ.lookups() if int(np.prod(op.shape)) > 64) * ex.words * 8 / 1e6:.0f}"
-                              f"-{max(int(np.prod(op.shape)) for op in circ.lookups()) * ex.words * 8 / 1e6:.0f} MB) several times between two uses of any buffer, and the "
+            "config": {"workload": CONFIGS[args.config][0], "config_id": args.config,
+                       "parallelism": (f"{world} replicas, one image per GPU" if replicas else f"layer-partitioned x{world}"),
+                       "pbs_per_image": cnt["total"], "pbs_tlu": cnt["tlu"], "pbs_bit": cnt["bit"], "conv_macs": circ.macs(),
+                       "accumulator_layout": ("one centred offset and one width per channel" if circ_layout(circ) == 2 else
+                                              "one centred offset per channel" if circ_layout(circ) == 1 else "tensor-wide offset and width (Concrete-like)")
+                                             + " (tfx_b200/circuit.py, DESIGN.md 3)",
+                       "tlu_set": str(tlu), "bit_set": str(bit),
+                       "l2": (f"no flush: every lookup layer streams its ciphertext tensor ({min(x for x in sizes if x > 64) * ex.words * 8 / 1e6:.0f}"
+                              f"-{max(sizes) * ex.words * 8 / 1e6:.0f} MB) several times between two uses of any buffer, and the "
                               f"{ex.keys.device_bytes / 1e6:.0f} MB of keys alternate per kernel; the working set per step exceeds L2 (126 MB)"),
                        "keygen_s": t_keygen, "key_bytes": ex.keys.device_bytes},
-            "pbs_per_sec_per_gpu": cnt["total"] / dev_s / world,
-            "e2e": {"value": e2e_s, "unit": UNIT, "h2d_bytes_per_step": host_in.numel() * 8, "d2h_bytes_per_step": host_out.numel() * 8},
+            "pbs_per_sec_per_gpu": cnt["total"] / dev_s / (1 if replicas else world),
+            "images_per_step": world if replicas else 1,
+            "e2e": {"value": e2e_s, "unit": UNIT, "h2d_bytes_per_step": n_in * 8, "d2h_bytes_per_step": n_out * 8,
+                    "call": "q_module.forward(numpy float32[1,C,H,W], fhe='execute') -> numpy (reference homomorphic_eval.py:70): host "
+                            "quantisation, H2D of the plaintext words, encryption, circuit, decryption, D2H of the phases, de-quantisation; "
+                            "host wall clock around the call, max over ranks"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {
-                "kernel": f"pbs_kernel<log2N={dom_p.N.bit_length() - 1},k={dom_p.k}> ({dom})",
-                "bound": "fp64", "achieved": flops / sec / 1e12, "peak": dfma / 1e12, "unit": "TFLOP/s",
-                "frac": flops / sec / dfma, "peak_source": "DFMA rate measured live by tfx_probe_rate (MEASURED_PEAKS.json has no FP64 figure)",
-                "flops_per_pbs": P.pbs_flops(dom_p), "pbs_per_launch": units / max(1, nl), "avg_launch_ms": sec / max(1, nl) * 1e3,
-                "share_of_step": sec / total_kernel_s,
-                "traffic": (prof.get(dom, {}).get("dram_bytes_per_unit") or 0) * units / max(1, nl) or None,
-                "traffic_source": prof.get("source"),
-                "hbm": {"achieved": nl * P.bsk_bytes(dom_p) / sec / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": nl * P.bsk_bytes(dom_p) / sec / 1e9 / hbm_peak, "peak_source": peak_src,
-                        "note": "algorithmic bootstrapping-key bytes per launch (one pass over the key serves the whole batch)"},
-            },
+            "roofline": pbs_roofline(dom, bit if dom == "pbs_bit" else tlu),
             "roofline_other_pbs_kernel": pbs_roofline("pbs_tlu" if dom == "pbs_bit" else "pbs_bit", tlu if dom == "pbs_bit" else bit),
             "kernel_breakdown_s_per_step": {k: v[0] / args.steps for k, v in ks.items()},
             "kernel_breakdown_note": ("CUDA-event time per kernel class on the launching stream" +
                                       ("; with N > 1 the two halves of a layer run on two streams, so class times overlap and sum to more than the step" if world > 1 else "")),
             "imac_peak_tmacs": imac / 1e12,
+            "output_sha": output_sha,
             "check": {"max_abs_deviation_from_clear": max_dev, "clear_output_span": span,
-                      "note": "p_error=0.01 per PBS makes execute != clear by design; tests/ hold the bit-exact parity checks"},
+                      "note": "p_error=0.01 per PBS makes execute != clear by design; tests/ hold the bit-exact parity checks; "
+                              "output_sha = sha256 of the output ciphertext words (identical at every N for the same config)"},
             "published_context": "reference README.md:84: 565 s on 96 CPU cores (Concrete CPU)",
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -307,6 +344,12 @@ def run_gpu(args):
     if world > 1:
         dist.destroy_process_group()
 
+
+def circ_layout(circ) -> int:
+    """2: per-channel offsets and widths, 1: per-channel offsets, 0: tensor-wide"""
+    per_w = any(getattr(op, "chan_bits", None) is not None for op in circ.ops)
+    per_o = any(isinstance(getattr(op, "offset", 0), np.ndarray) and np.unique(op.offset).size > 1 for op in circ.ops)
+    return 2 if per_w else 1 if per_o else 0
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -358,6 +401,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="tfx", choices=["tfx", "reference"])
+    ap.add_argument("--config", type=int, default=1, choices=sorted(CONFIGS), help="BASELINE.json configuration (1 = headline)")
     ap.add_argument("--cpu-sample", type=int, default=256, help="ciphertexts per CPU sample step (about 10 s of host work on 16 threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--preprocess", action="store_true", help="measure the DCT preprocessing row instead of the encrypted circuit")

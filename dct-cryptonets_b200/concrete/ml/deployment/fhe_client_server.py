@@ -11,7 +11,6 @@ import hashlib
 import io
 import json
 import os
-import pickle
 import struct
 import zipfile
 from typing import Optional
@@ -71,20 +70,23 @@ class FHEModelDev:
     def save(self, via_mlir: bool = False):
         os.makedirs(self.path_dir, exist_ok=True)
         fc = self.model.fhe_circuit
-        payload = pickle.dumps({"circuit": fc.circuit, "params": _params_to_json(fc.params)})
+        head, arrays = C.circuit_to_portable(fc.circuit)
+        payload = _pack({"kind": "circuit", "circuit": head, "params": _params_to_json(fc.params)}, arrays)
         for name in ("client.zip", "server.zip"):
             path = os.path.join(self.path_dir, name)
             if os.path.exists(path):
                 raise FileExistsError(f"{path} already exists")
             with zipfile.ZipFile(path, "w") as z:
-                z.writestr("circuit.pkl", payload)
+                z.writestr("circuit.tfxb", payload)           # JSON header + raw arrays: loading a bundle executes no code
                 z.writestr("versions.json", json.dumps({"tfx_b200": _VERSION}))
 
 
 def _load_bundle(path_dir: str, name: str):
     with zipfile.ZipFile(os.path.join(path_dir, name)) as z:
-        d = pickle.loads(z.read("circuit.pkl"))
-    return d["circuit"], _params_from_json(d["params"])
+        header, arrays = _unpack(z.read("circuit.tfxb"))
+    if header.get("kind") != "circuit":
+        raise ValueError("expected a circuit bundle")
+    return C.circuit_from_portable(header["circuit"], arrays), _params_from_json(header["params"])
 
 
 class FHEModelClient:
@@ -92,8 +94,6 @@ class FHEModelClient:
         self.path_dir, self.key_dir = path_dir, key_dir
         self.circuit, self.params = _load_bundle(path_dir, "client.zip")
         self._ex: Optional[CircuitExecutor] = None
-        self.key_seed = int.from_bytes(os.urandom(16), "little")
-        self._enc_counter = 0
 
     def _executor(self) -> CircuitExecutor:
         if self._ex is None:
@@ -103,7 +103,7 @@ class FHEModelClient:
     def generate_private_and_evaluation_keys(self, force: bool = False):
         ex = self._executor()
         if ex.keys is None or force:
-            ex.keygen(self.key_seed)
+            ex.keygen()                        # fresh 16 bytes from the OS CSPRNG (executor.keygen)
 
     def get_serialized_evaluation_keys(self) -> bytes:
         self.generate_private_and_evaluation_keys()
@@ -118,8 +118,9 @@ class FHEModelClient:
         ex = self._executor()
         q = C.quantize_input(self.circuit, np.asarray(x))
         assert q.shape[0] == 1, "one sample per call"
-        self._enc_counter += 1
-        cts = ex.encrypt(q[0], enc_seed=(self.key_seed ^ (self._enc_counter * 0x9E3779B97F4A7C15)) % (1 << 128))
+        # encryption randomness: its own os.urandom seed per key set (independent of the key seed) with a PRF index that
+        # advances by the ciphertexts produced so far (executor.encrypt) — masks never repeat, not even across calls
+        cts = ex.encrypt(q[0])
         return _pack({"kind": "ciphertexts", "width": self.circuit.input_width}, [ex.ctx.to_host_u64(cts)])
 
     def deserialize_decrypt(self, blob: bytes) -> np.ndarray:
@@ -145,13 +146,15 @@ class FHEModelServer:
         self.circuit, self.params = _load_bundle(self.path_dir, "server.zip")
 
     def _install_keys(self, blob: bytes):
-        digest = hashlib.sha256(blob[:1 << 20]).hexdigest() + str(len(blob))
+        digest = hashlib.sha256(blob).hexdigest()              # the whole blob: two key sets never share a digest
         if self._ex is not None and digest == self._key_digest:
             return
         header, arrays = _unpack(blob)
         if header.get("kind") != "evaluation_keys":
             raise ValueError("expected serialized evaluation keys")
         params = _params_from_json(header["params"])
+        if self._ex is not None and list(self._ex.params) != list(params):
+            self._ex = None                                    # another client's parameter sets: rebuild the executor
         if self._ex is None:
             self._ex = CircuitExecutor(self.circuit, params)
         ks = KeySet.empty(self._ex.ctx, params)

@@ -134,7 +134,7 @@ static int get_tables(tfx_ctx* ctx, uint32_t N, FftTables** out) {
     cudaError_t e = cudaMalloc(&t.tw_d, bytes); if (e != cudaSuccess) return set_cuda_error(e, "cudaMalloc(tw)");
     e = cudaMemcpyAsync(t.tw_d, tw.data(), bytes, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);       // host vectors die at scope exit
-    if (e != cudaSuccess) return set_cuda_error(e, "upload fft tables");
+    if (e != cudaSuccess) { cudaFree(t.tw_d); return set_cuda_error(e, "upload fft tables"); }
     ctx->tables.push_back(t);
     *out = &ctx->tables.back();
     return TFX_OK;

@@ -99,8 +99,9 @@ __global__ void __launch_bounds__(CV_THREADS) conv2d_kernel(ConvArgs a) {
     }
 }
 
-__global__ void axpby_kernel(const uint64_t* __restrict__ a, uint64_t sa, const uint64_t* __restrict__ b, uint64_t sb,
-                             uint64_t body_const, size_t count, uint32_t words, uint64_t* __restrict__ out) {
+// no __restrict__: include/tfx.h allows out to alias a or b (element i is read before it is written, by the same thread)
+__global__ void axpby_kernel(const uint64_t* a, uint64_t sa, const uint64_t* b, uint64_t sb,
+                             uint64_t body_const, size_t count, uint32_t words, uint64_t* out) {
     const size_t total = count * words;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         uint64_t v = a[i] * sa;

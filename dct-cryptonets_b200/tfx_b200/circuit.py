@@ -212,6 +212,84 @@ class Circuit:
 # --------------------------------------------------------------------------------------------------------
 # Clear integer evaluator (exact semantics of the circuit; also the noise-free model behind fhe='simulate')
 # --------------------------------------------------------------------------------------------------------
+# --------------------------------------------------------------------------------------------------------
+# Serialisation: JSON header + raw arrays (no pickle: a bundle comes from the model provider and is opened by the
+# process that holds the secret key).  Unknown op kinds or fields are rejected.
+# --------------------------------------------------------------------------------------------------------
+_OP_CLASSES = {"conv": ConvOp, "add": AddOp, "fadd": FusedAddOp, "tlu": TluOp}
+_TUPLE_FIELDS = {"in_shape", "out_shape", "shape", "input_shape", "output_shape"}
+
+
+def _enc_value(v, arrays: list):
+    if isinstance(v, np.ndarray):
+        arrays.append(np.ascontiguousarray(v))
+        return {"__array__": len(arrays) - 1}
+    if isinstance(v, QuantInfo):
+        return {"__quant__": [float(v.scale), int(v.qmin), int(v.qmax)]}
+    if isinstance(v, (tuple, list)):
+        return [_enc_value(x, arrays) for x in v]
+    if isinstance(v, (np.integer,)):
+        return int(v)
+    if isinstance(v, (np.floating,)):
+        return float(v)
+    if v is None or isinstance(v, (bool, int, float, str)):
+        return v
+    raise TypeError(f"cannot serialise a {type(v).__name__} in a circuit")
+
+
+def _dec_value(v, arrays: list, name: str):
+    if isinstance(v, dict):
+        if set(v) == {"__array__"}:
+            return np.array(arrays[int(v["__array__"])])          # own, writable copy
+        if set(v) == {"__quant__"}:
+            sc, lo, hi = v["__quant__"]
+            return QuantInfo(float(sc), int(lo), int(hi))
+        raise ValueError(f"unknown object in circuit field {name!r}")
+    if isinstance(v, list):
+        seq = [_dec_value(x, arrays, name) for x in v]
+        return tuple(seq) if name in _TUPLE_FIELDS else seq
+    return v
+
+
+def circuit_to_portable(circ: "Circuit"):
+    """-> (JSON-able header, list of numpy arrays)"""
+    import dataclasses
+    arrays: list = []
+    head = {}
+    for f in dataclasses.fields(Circuit):
+        if f.name == "ops":
+            continue
+        head[f.name] = _enc_value(getattr(circ, f.name), arrays)
+    ops = []
+    for op in circ.ops:
+        d = {"kind": op.kind}
+        for f in dataclasses.fields(type(op)):
+            if f.name != "kind":
+                d[f.name] = _enc_value(getattr(op, f.name), arrays)
+        ops.append(d)
+    head["ops"] = ops
+    return head, arrays
+
+
+def circuit_from_portable(head: dict, arrays: list) -> "Circuit":
+    import dataclasses
+    head = dict(head)
+    ops = []
+    for d in head.pop("ops"):
+        d = dict(d)
+        cls = _OP_CLASSES.get(d.pop("kind", None))
+        if cls is None:
+            raise ValueError("unknown op kind in circuit bundle")
+        names = {f.name for f in dataclasses.fields(cls)} - {"kind"}
+        if set(d) - names:
+            raise ValueError(f"unknown fields in {cls.__name__}: {sorted(set(d) - names)}")
+        ops.append(cls(**{k: _dec_value(v, arrays, k) for k, v in d.items()}))
+    names = {f.name for f in dataclasses.fields(Circuit)} - {"ops"}
+    if set(head) - names:
+        raise ValueError(f"unknown fields in Circuit: {sorted(set(head) - names)}")
+    return Circuit(ops=ops, **{k: _dec_value(v, arrays, k) for k, v in head.items()})
+
+
 def _int_conv(x: np.ndarray, op: ConvOp, weight: np.ndarray) -> np.ndarray:
     """x: int64 [B][C][H][W] -> int64; float64 conv is exact for these magnitudes (< 2^53)."""
     xt = torch.from_numpy(x.astype(np.float64))
@@ -435,6 +513,8 @@ class CircuitBuilder:
         self.model = model.eval()
         # opt-in (TFX_FUSE_RESIDUAL=1 for A/B runs): validated against the oracle on the CPU only, never run on a GPU yet
         self.fuse_residual = fuse_residual or os.environ.get("TFX_FUSE_RESIDUAL", "0") == "1"
+        if os.environ.get("TFX_PER_CHANNEL_OFFSETS", "1") == "0":   # A/B knob: the Concrete-like tensor-wide layout
+            per_channel_offsets, per_channel_widths = False, False
         if per_channel_widths is None:                       # default on; TFX_PER_CHANNEL_WIDTHS=0 switches it off for A/B measurements
             per_channel_widths = per_channel_offsets and os.environ.get("TFX_PER_CHANNEL_WIDTHS", "1") != "0"
         if per_channel_widths and not per_channel_offsets:

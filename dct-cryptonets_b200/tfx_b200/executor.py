@@ -163,26 +163,60 @@ class CircuitExecutor:
         return np.zeros(channels, dtype=np.int64)
 
     # ---- keys ------------------------------------------------------------------------------------------------
-    def keygen(self, seed=1, keep_standard_bsk: bool = False) -> float:
+    def _fresh_seed(self) -> bytes:
+        """16 bytes from the OS CSPRNG; with several ranks rank 0 draws and every rank receives the same bytes (the keys
+        and the input ciphertexts are replicated)"""
+        seed = os.urandom(16)
+        if self.world > 1:
+            import torch.distributed as dist
+            box = [seed]
+            dist.broadcast_object_list(box, src=dist.get_global_rank(self.pg, 0) if self.pg is not None else 0, group=self.pg)
+            seed = box[0]
+        return seed
+
+    def _bind_stream(self):
+        """library kernels and the torch ops around them (gathers, permutations, NCCL) must share one stream: follow
+        torch's current stream on every entry point instead of the one that was current at construction"""
+        if self.ctx.device.type == "cuda":                 # (tests drive the host logic with a CPU stand-in context)
+            self.ctx.set_stream(torch.cuda.current_stream(self.ctx.device))
+
+    def keygen(self, seed=None, keep_standard_bsk: bool = False) -> float:
+        """seed: 16 bytes or an int; None (the default) draws a fresh one from the OS CSPRNG like Concrete's keygen.
+        A fixed seed is for tests and benchmarks only: the secret keys are a deterministic function of it."""
         t0 = time.time()
+        self._bind_stream()
         if self.keys is not None:
             self.keys.close()
+        if seed is None:
+            seed = self._fresh_seed()
         self.keys = KeySet.generate(self.ctx, self.params, seed, keep_standard_bsk)
+        self._enc_seed, self._enc_next = None, 0
         self.ctx.synchronize()
         return time.time() - t0
 
     def use_keys(self, keys: KeySet):
         self.keys = keys
+        self._enc_seed, self._enc_next = None, 0
 
     # ---- client side -------------------------------------------------------------------------------------------
-    def encrypt(self, q_in: np.ndarray, enc_seed=2) -> torch.Tensor:
-        """q_in int64 [C][H][W] -> ciphertexts int64-view u64 [C*H*W][big_dim+1] at the input encoding width"""
+    def encrypt(self, q_in: np.ndarray, enc_seed=None, first_index: Optional[int] = None) -> torch.Tensor:
+        """q_in int64 [C][H][W] -> ciphertexts int64-view u64 [C*H*W][big_dim+1] at the input encoding width.
+        enc_seed None (the default): masks and noise come from a per-key-set random seed whose PRF index advances by the
+        number of ciphertexts already produced, so no two ciphertexts ever share a mask.  An explicit enc_seed (tests,
+        benchmarks) reproduces the same ciphertexts on every call."""
+        self._bind_stream()
         delta_shift = 63 - self.circ.input_width
         pts = (q_in.astype(np.int64).reshape(-1).view(np.uint64) << np.uint64(delta_shift))
         d_pts = self.ctx.to_device_u64(pts)
-        return self.keys.encrypt(d_pts, self.input_std, enc_seed)
+        if enc_seed is None:
+            if getattr(self, "_enc_seed", None) is None:
+                self._enc_seed, self._enc_next = self._fresh_seed(), 0
+            enc_seed, first_index = self._enc_seed, self._enc_next
+            self._enc_next += int(pts.size)
+        return self.keys.encrypt(d_pts, self.input_std, enc_seed, first_index or 0)
 
     def decrypt(self, cts: torch.Tensor) -> np.ndarray:
+        self._bind_stream()
         ph = self.ctx.to_host_u64(self.keys.phase(cts))
         w = self.circ.output_width
         shift = np.uint64(63 - w)
@@ -221,6 +255,7 @@ class CircuitExecutor:
         """in_cts [Cin*H*W][words] -> output ciphertexts [n_out][words].  Enqueues on the context stream."""
         circ, ctx, keys = self.circ, self.ctx, self.keys
         assert keys is not None, "keygen() first"
+        self._bind_stream()
         words = self.words
         prof = profile_kernels and stats is not None
         if prof and stats.kernel_events is None:

@@ -29,9 +29,14 @@ class FheCircuit:
         self.parameter_info = info
         self.graph = _Graph(circ)
         self.executor = None
-        self.key_seed = 1
-        self.encryption_seed = 2
+        # None = drawn from the OS CSPRNG (keys at keygen, encryption masks per key set with a running PRF index);
+        # fixed values only through keygen(seed=..., encryption_seed=...) for tests and benchmarks
+        self.key_seed = None
+        self.encryption_seed = None
         self.last_run_stats = None
+        self.last_run_events = None        # CUDA events around executor.run (device time of the server-side step)
+        self.last_output = None            # output ciphertexts of the last run (device tensor)
+        self.profile_kernels = False       # bench.py: per-kernel-class CUDA events in last_run_stats
         self._dist = None
 
     @property
@@ -71,7 +76,12 @@ class FheCircuit:
     def run(self, cts):
         from .executor import RunStats
         self.last_run_stats = RunStats()
-        return self.executor.run(cts, self.last_run_stats)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = self.executor.run(cts, self.last_run_stats, profile_kernels=self.profile_kernels)
+        e1.record()
+        self.last_run_events, self.last_output = (e0, e1), out
+        return out
 
     def decrypt(self, cts) -> np.ndarray:
         return self.executor.decrypt(cts)

@@ -215,3 +215,9 @@ def axpby(a, sa: int, b=None, sb: int = 0, body_const: int = 0) -> np.ndarray:
 
 def num_threads() -> int:
     return int(lib().orc_num_threads())
+
+
+def set_num_threads(n: int) -> int:
+    """size of the OpenMP team for every later call (bench.py: all host cores, whatever OMP_NUM_THREADS says)"""
+    lib().orc_set_num_threads(C.c_int(int(n)))
+    return num_threads()

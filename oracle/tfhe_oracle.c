@@ -662,3 +662,13 @@ ORC_API int orc_num_threads(void) {
     return 1;
 #endif
 }
+
+/* torchrun exports OMP_NUM_THREADS=1 when it starts more than one process per node: the timing legs set the team size
+ * explicitly instead of inheriting it */
+ORC_API void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}

@@ -213,6 +213,32 @@ def test_wire_format_roundtrip():
         _unpack(b"nope" + bytes(20))
 
 
+def test_circuit_bundle_is_pickle_free_and_lossless(tiny, tmp_path):
+    """client.zip / server.zip carry the circuit as a JSON header + raw arrays: loading one executes no code (a bundle comes
+    from the model provider and is opened by the process that holds the secret key), and the circuit survives unchanged."""
+    import zipfile
+    from types import SimpleNamespace
+    from concrete.ml.deployment.fhe_client_server import FHEModelDev, _load_bundle, _pack
+    m, calib, circ = tiny
+    fused = C.build_circuit(m, calib, 5, 6, 0.01, fuse_residual=True)
+    tlu, bit, _ = P.pick_parameters(circ.noise_spec())
+    x = C.quantize_input(circ, calib[:4].numpy())
+    for i, cc in enumerate((circ, fused)):
+        d = tmp_path / f"bundle{i}"
+        FHEModelDev(str(d), SimpleNamespace(fhe_circuit=SimpleNamespace(circuit=cc, params=(tlu, bit)))).save()
+        with zipfile.ZipFile(d / "client.zip") as z:
+            assert not any(n.endswith(".pkl") for n in z.namelist())
+        for name in ("client.zip", "server.zip"):
+            c2, params = _load_bundle(str(d), name)
+            assert list(params) == [tlu, bit]
+            assert c2.to_text() == cc.to_text()
+            assert np.array_equal(C.evaluate_clear(c2, x), C.evaluate_clear(cc, x))
+    head, arrays = C.circuit_to_portable(circ)
+    head["ops"][0]["evil"] = 1
+    with pytest.raises(ValueError):
+        C.circuit_from_portable(head, arrays)
+
+
 REF = "/root/reference/dct-cryptonets"
 
 
