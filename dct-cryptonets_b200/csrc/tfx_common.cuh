@@ -343,7 +343,7 @@ __device__ __forceinline__ void fft_forward_regs2(double2 (&xa)[8], double2 (&xb
     if constexpr (PL::P >= 3) {
         TFX_STORE2(1)
         TFX_TW(2)
-        wsync();
+        if constexpr (LOGM >= 12) sync(); else wsync();   // M = 4096: pass 1 spans the points of a warp pair
         TFX_LOAD2(2)
         TFX_PASS2(2, false)
     }
@@ -376,7 +376,7 @@ __device__ __forceinline__ void fft_inverse_regs2(double2 (&xa)[8], double2 (&xb
         TFX_STORE2(2)
     }
     TFX_TW(1)
-    wsync();
+    if constexpr (LOGM >= 12) sync(); else wsync();
     TFX_LOAD2(1)
     TFX_PASS2(1, true)
     TFX_STORE2(1)
@@ -389,6 +389,82 @@ __device__ __forceinline__ void fft_inverse_regs2(double2 (&xa)[8], double2 (&xb
 #undef TFX_PASS2
 #undef TFX_STORE2
 #undef TFX_LOAD2
+
+// ---- NT transforms interleaved in one thread (round 2): every transform has its own buffer bufs + q*M, twiddles are
+// loaded once per pass for all NT.  The arithmetic per transform is exactly that of fft_forward_regs2 / fft_inverse_regs2.
+// Buffer protocol (the caller owns the CTA-level ordering): on entry to fft_forward_multi nobody reads or writes the
+// buffers any more (the caller's end-of-step barrier); after the one CTA barrier inside, a warp only touches the points it
+// owns (index >> 8 == warp), so everything up to and including fft_inverse_multi's last warp-local pass needs __syncwarp only.
+template <int LOGM, int NT, typename SYNC_CTA, typename SYNC_WARP>
+__device__ __forceinline__ void fft_forward_multi(double2 (&x)[NT][8], double2 (&w)[7], int t, double2* __restrict__ bufs,
+                                                  const double2* __restrict__ tw, SYNC_CTA sync, SYNC_WARP wsync) {
+    using PL = FftPlan<LOGM>;
+    constexpr int M = 1 << LOGM;
+#pragma unroll
+    for (int q = 0; q < NT; q++) pass_nodes<LOGM, 0, false>(x[q], w);
+    load_tw<LOGM, 1>(w, t, tw);
+#pragma unroll
+    for (int q = 0; q < NT; q++) pass_store<LOGM, 0>(x[q], t, bufs + q * M);
+    sync();
+#pragma unroll
+    for (int q = 0; q < NT; q++) pass_load<LOGM, 1>(x[q], t, bufs + q * M);
+#pragma unroll
+    for (int q = 0; q < NT; q++) pass_nodes<LOGM, 1, false>(x[q], w);
+    if constexpr (PL::P >= 3) {
+#pragma unroll
+        for (int q = 0; q < NT; q++) pass_store<LOGM, 1>(x[q], t, bufs + q * M);
+        load_tw<LOGM, 2>(w, t, tw);
+        if constexpr (LOGM >= 12) sync(); else wsync();
+#pragma unroll
+        for (int q = 0; q < NT; q++) pass_load<LOGM, 2>(x[q], t, bufs + q * M);
+#pragma unroll
+        for (int q = 0; q < NT; q++) pass_nodes<LOGM, 2, false>(x[q], w);
+    }
+    if constexpr (PL::P >= 4) {
+#pragma unroll
+        for (int q = 0; q < NT; q++) pass_store<LOGM, 2>(x[q], t, bufs + q * M);
+        load_tw<LOGM, 3>(w, t, tw);
+        wsync();
+#pragma unroll
+        for (int q = 0; q < NT; q++) pass_load<LOGM, 3>(x[q], t, bufs + q * M);
+#pragma unroll
+        for (int q = 0; q < NT; q++) pass_nodes<LOGM, 3, false>(x[q], w);
+    }
+}
+
+// inverse, all passes BELOW the last one: the caller has run the last pass's nodes on every spectrum and stored it with
+// pass_store<LOGM, LAST> into bufs + q*M (lane-private positions).  On return y[q][e] = coefficient pair t + e*TPF (no 1/M).
+template <int LOGM, int NT, typename SYNC_CTA, typename SYNC_WARP>
+__device__ __forceinline__ void fft_inverse_multi_rest(double2 (&y)[NT][8], int t, double2* __restrict__ bufs,
+                                                       const double2* __restrict__ tw, SYNC_CTA sync, SYNC_WARP wsync) {
+    using PL = FftPlan<LOGM>;
+    constexpr int M = 1 << LOGM;
+    double2 w[7];
+    if constexpr (PL::P >= 4) {
+        load_tw<LOGM, 2>(w, t, tw);
+        wsync();
+#pragma unroll
+        for (int q = 0; q < NT; q++) pass_load<LOGM, 2>(y[q], t, bufs + q * M);
+#pragma unroll
+        for (int q = 0; q < NT; q++) pass_nodes<LOGM, 2, true>(y[q], w);
+#pragma unroll
+        for (int q = 0; q < NT; q++) pass_store<LOGM, 2>(y[q], t, bufs + q * M);
+    }
+    load_tw<LOGM, 1>(w, t, tw);
+    if constexpr (LOGM >= 12) sync(); else wsync();
+#pragma unroll
+    for (int q = 0; q < NT; q++) pass_load<LOGM, 1>(y[q], t, bufs + q * M);
+#pragma unroll
+    for (int q = 0; q < NT; q++) pass_nodes<LOGM, 1, true>(y[q], w);
+#pragma unroll
+    for (int q = 0; q < NT; q++) pass_store<LOGM, 1>(y[q], t, bufs + q * M);
+    load_tw<LOGM, 0>(w, t, tw);
+    sync();
+#pragma unroll
+    for (int q = 0; q < NT; q++) pass_load<LOGM, 0>(y[q], t, bufs + q * M);
+#pragma unroll
+    for (int q = 0; q < NT; q++) pass_nodes<LOGM, 0, true>(y[q], w);
+}
 
 // canonical transform position of element e of thread t after the last forward pass
 template <int LOGM>

@@ -9,6 +9,7 @@
 // thread-major layout (coalesced 16 B per lane) and accumulates the (k+1) output spectra in registers; then the
 // (k+1) inverse FFTs run from those registers and add the rounded result into the accumulator.
 // Replaces (upstream) concrete-cpu's bootstrap behind reference homomorphic_eval.py:70.
+#include <stdio.h>
 #include <stdlib.h>
 #include "tfx_common.cuh"
 #include "tfx_internal.h"
@@ -24,8 +25,10 @@ template <int LOGN, int K> struct PbsCfg {
     static constexpr int THREADS = TPF;
     // accumulator + two transform buffers (one per interleaved transform) + node twiddle table + the hand-out slot
     // (kept in the dynamic allocation: a static __shared__ word on top of a 227 KB dynamic limit is rejected)
+    // N = 8192 (7-bit lookups): accumulator 128 KB + one transform buffer 64 KB; the 64 KB twiddle table stays in global memory
+    static constexpr bool TW_SMEM = (LOGN <= 12);
     static constexpr size_t smem_bytes(int) {
-        return (size_t)G * N * 8 + (size_t)M * 16 * (DUAL ? 2 : 1) + (size_t)M * 16 + 16;
+        return (size_t)G * N * 8 + (size_t)M * 16 * (DUAL ? 2 : 1) + (TW_SMEM ? (size_t)M * 16 : 0) + 16;
     }
     // Two transforms interleaved per thread (more ILP, one more buffer) or one at a time.  Measured (profiles/r01_pbs_experiments.md):
     // interleaving wins 13 % for (k=1, N=2048, l=2) — four forward and two inverse transforms pair up — and loses 6 % for
@@ -35,7 +38,7 @@ template <int LOGN, int K> struct PbsCfg {
 #elif defined(TFX_PBS_DUAL)
     static constexpr bool DUAL = true;
 #else
-    static constexpr bool DUAL = !(K == 2 && LOGN <= 10);
+    static constexpr bool DUAL = !(K == 2 && LOGN <= 10) && LOGN <= 12;
 #endif
     static constexpr int MIN_BLOCKS = (LOGN <= 11) ? 2 : 1;
 };
@@ -82,8 +85,9 @@ pbs_kernel(PbsArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* acc = reinterpret_cast<uint64_t*>(smem_raw);                    // [G][N]
     double2* bufs = reinterpret_cast<double2*>(acc + (size_t)G * N);          // [2][M] swizzled, alternate per transform
-    double2* s_tw = bufs + (C::DUAL ? 2 : 1) * M;                             // [M]
-    volatile uint32_t* s_ct = reinterpret_cast<volatile uint32_t*>(s_tw + M);  // next ciphertext index (dynamic hand-out)
+    double2* s_twbuf = bufs + (C::DUAL ? 2 : 1) * M;                          // [M] (absent when the table stays in global memory)
+    const double2* s_tw = C::TW_SMEM ? s_twbuf : a.tw;
+    volatile uint32_t* s_ct = reinterpret_cast<volatile uint32_t*>(s_twbuf + (C::TW_SMEM ? M : 0));  // next ciphertext index (dynamic hand-out)
 
     const int t = threadIdx.x;
     auto sync = [] { __syncthreads(); };
@@ -91,7 +95,7 @@ pbs_kernel(PbsArgs a) {
     double2* bufa = bufs;
     double2* bufb = C::DUAL ? bufs + M : bufs;
 
-    for (int i = t; i < M; i += TPF) s_tw[i] = a.tw[i];
+    if constexpr (C::TW_SMEM) for (int i = t; i < M; i += TPF) s_twbuf[i] = a.tw[i];
 
     DigitCtx dc;
     {
@@ -316,6 +320,171 @@ pbs_kernel(PbsArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// v8 (round 2): all (k+1)*l forward transforms of a CMux step run interleaved in one instruction stream (one buffer per
+// transform, node twiddles fetched once per pass for all of them, independent dependency chains for the scheduler), the
+// Fourier MAC produces one output spectrum at a time and runs its first inverse pass at once, and the remaining inverse
+// passes of the (k+1) outputs run interleaved again.  Three CTA barriers per step instead of seven.  Rotation and gadget
+// decomposition work on the high 32 bits only (base_log * level <= 31: the rounding constant has no low word).
+// Arithmetic per value is identical to pbs_kernel (same node sequence, same FMA chain over (r, level) ascending).
+// ---------------------------------------------------------------------------------------------------
+template <int LOGN, int K, int LEVEL> struct PbsCfg8 {
+    static constexpr int N = 1 << LOGN, LOGM = LOGN - 1, M = N / 2, TPF = M / 8, G = K + 1, NF = G * LEVEL;
+    static constexpr size_t SMEM = (size_t)G * N * 8 + (size_t)NF * M * 16 + (size_t)M * 16;
+    static constexpr int MIN_BLOCKS = (LOGN <= 10) ? 4 : (LOGN == 11 ? 2 : 1);
+};
+
+template <int LOGN, int K, int LEVEL>
+__global__ void __launch_bounds__(PbsCfg8<LOGN, K, LEVEL>::TPF, PbsCfg8<LOGN, K, LEVEL>::MIN_BLOCKS)
+pbs_kernel_v8(PbsArgs a) {
+    using C = PbsCfg8<LOGN, K, LEVEL>;
+    constexpr int N = C::N, M = C::M, LOGM = C::LOGM, TPF = C::TPF, G = C::G, NF = C::NF;
+    constexpr int LAST = FftPlan<LOGM>::P - 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* acc = reinterpret_cast<uint64_t*>(smem_raw);                    // [G][N]
+    double2* bufs = reinterpret_cast<double2*>(acc + (size_t)G * N);          // [NF][M] swizzled, one per interleaved transform
+    double2* s_tw = bufs + (size_t)NF * M;                                    // [M]; entry M-1 is not a twiddle:
+    volatile uint32_t* s_ct = reinterpret_cast<volatile uint32_t*>(s_tw + (M - 1));   // it holds the hand-out slot
+
+    const int t = threadIdx.x;
+    auto sync = [] { __syncthreads(); };
+    auto wsync = [] { __syncwarp(); };
+    for (int i = t; i < M - 1; i += TPF) s_tw[i] = a.tw[i];
+
+    // gadget constants, 32-bit: v = top (base_log * LEVEL) bits of the rounded word
+    const int total = a.base_log * LEVEL;
+    const int rsh = 32 - total;
+    const uint32_t radd_hi = 1u << (31 - total);
+    const uint32_t dmask = (1u << a.base_log) - 1u, dhalf = 1u << (a.base_log - 1);
+    uint32_t lvl_shift[LEVEL], lvl_lowmask[LEVEL], lvl_thr[LEVEL];
+#pragma unroll
+    for (int lvl = 0; lvl < LEVEL; lvl++) {
+        const int sh = a.base_log * (LEVEL - 1 - lvl);
+        lvl_shift[lvl] = (uint32_t)sh;
+        lvl_lowmask[lvl] = sh > 0 ? ((1u << sh) - 1u) : 0u;
+        uint32_t rep = 0;
+        for (int q = 0; q < LEVEL - 1 - lvl; q++) rep = (rep << a.base_log) | 1u;
+        lvl_thr[lvl] = sh > 0 ? (dhalf - 1u) * rep + 1u : 0xffffffffu;
+    }
+    // exact int32 -> double: bits (0x43300000, sd ^ 0x80000000) are 2^52 + 2^31 + sd
+    auto i2d = [](int32_t sd) { return __hiloint2double(0x43300000, sd ^ (int)0x80000000) - 4503601774854144.0; };
+    auto digits_of = [&](uint64_t d, double (&out)[LEVEL]) {
+        const uint32_t hi = (uint32_t)(d >> 32) + radd_hi;
+        if constexpr (LEVEL == 1) {
+            out[0] = i2d((int32_t)hi >> rsh);
+        } else {
+            const uint32_t v = hi >> rsh;
+#pragma unroll
+            for (int lvl = 0; lvl < LEVEL; lvl++) {
+                uint32_t dg = (v >> lvl_shift[lvl]) & dmask;
+                dg += ((v & lvl_lowmask[lvl]) >= lvl_thr[lvl]) ? 1u : 0u;
+                int32_t sd = (int32_t)dg;
+                if (dg >= dhalf) sd -= (int32_t)(dmask + 1u);
+                out[lvl] = i2d(sd);
+            }
+        }
+    };
+
+    for (;;) {
+        __syncthreads();
+        if (t == 0) *s_ct = atomicAdd(a.work_counter, 1u);
+        __syncthreads();
+        const uint32_t ct = *s_ct;
+        if (ct >= a.count) break;
+        const uint64_t* in = a.in + (size_t)ct * (a.n + 1);
+        {   // acc = X^{-bhat} * (0, .., 0, LUT)
+            const uint64_t* lut = a.luts + (size_t)a.lut_index[ct] * N;
+            const uint32_t bhat = mod_switch(__ldg(in + a.n), LOGN + 1);
+            for (int j = t; j < K * N; j += TPF) acc[j] = 0;
+            for (int j = t; j < N; j += TPF) {
+                uint32_t idx = (j + bhat) & (2 * N - 1);
+                acc[(size_t)K * N + j] = idx < N ? lut[idx] : (uint64_t)0 - lut[idx - N];
+            }
+        }
+        __syncthreads();
+
+        uint64_t a_next = __ldg(in);
+        for (uint32_t i = 0; i < a.n; i++) {
+            const uint32_t ahat = mod_switch(a_next, LOGN + 1);
+            a_next = __ldg(in + i + 1);
+            if (ahat == 0) continue;                                   // CTA-uniform
+            const double2* key_i = a.bsk + (size_t)i * NF * G * M + t;
+
+            double2 x[NF][8], w[7];
+            load_tw<LOGM, 0>(w, t, s_tw);
+            // rotation + decomposition: coefficient pairs (j, j + M) of X^ahat * acc_r - acc_r, all levels at once
+#pragma unroll
+            for (int r = 0; r < G; r++) {
+                const uint64_t* ar = acc + (size_t)r * N;
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    const int jc = t + e * TPF;
+                    const uint32_t s0 = (uint32_t)(jc - (int)ahat) & (2 * N - 1);
+                    const uint32_t s1 = s0 + M;                        // bit LOGN of s0 / s1 = sign of the wrapped coefficient
+                    const uint64_t m0 = (uint64_t)0 - (uint64_t)((s0 >> LOGN) & 1u), m1 = (uint64_t)0 - (uint64_t)((s1 >> LOGN) & 1u);
+                    const uint64_t d0 = ((ar[s0 & (N - 1)] ^ m0) - m0) - ar[jc];
+                    const uint64_t d1 = ((ar[s1 & (N - 1)] ^ m1) - m1) - ar[jc + M];
+                    double g0[LEVEL], g1[LEVEL];
+                    digits_of(d0, g0);
+                    digits_of(d1, g1);
+#pragma unroll
+                    for (int lvl = 0; lvl < LEVEL; lvl++) x[r * LEVEL + lvl][e] = make_double2(g0[lvl], g1[lvl]);
+                }
+            }
+            fft_forward_multi<LOGM, NF>(x, w, t, bufs, s_tw, sync, wsync);   // w now holds the last pass's twiddles
+
+            // Fourier MAC, one output component at a time (fma chain over f = r * l + lvl ascending), then that spectrum's
+            // first inverse pass (the same node twiddles, conjugated) and its store for the interleaved remainder
+#pragma unroll
+            for (int c = 0; c < G; c++) {
+                double2 o[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) o[e] = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int f = 0; f < NF; f++) {
+                    const double2* krow = key_i + ((size_t)f * G + c) * M;
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        const double2 kv = __ldg(krow + e * TPF);
+                        double re = o[e].x, im = o[e].y;
+                        re = fma(x[f][e].x, kv.x, re); re = fma(-x[f][e].y, kv.y, re);
+                        im = fma(x[f][e].x, kv.y, im); im = fma(x[f][e].y, kv.x, im);
+                        o[e] = make_double2(re, im);
+                    }
+                }
+                pass_nodes<LOGM, LAST, true>(o, w);
+                pass_store<LOGM, LAST>(o, t, bufs + (size_t)c * M);
+            }
+            double2 y[G][8];
+            fft_inverse_multi_rest<LOGM, G>(y, t, bufs, s_tw, sync, wsync);
+#pragma unroll
+            for (int c = 0; c < G; c++) {
+                uint64_t* ac = acc + (size_t)c * N;
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    const int jc = t + e * TPF;                          // the key carries the 1/M of the inverse transform
+                    ac[jc] += double_to_torus(y[c][e].x);
+                    ac[jc + M] += double_to_torus(y[c][e].y);
+                }
+            }
+            __syncthreads();                                           // accumulator complete, buffers free
+        }
+
+        uint64_t* o = a.out + (size_t)ct * ((size_t)a.big_dim + 1);
+        for (int j = t; j < K * N; j += TPF) {
+            int comp = j / N, tt = j - comp * N;
+            const uint64_t* ar = acc + (size_t)comp * N;
+            uint64_t v = (tt == 0) ? ar[0] : (uint64_t)0 - ar[N - tt];
+            if (a.mode == 0) o[j] = v; else o[j] -= v;
+        }
+        if (a.mode == 0) for (uint32_t j = K * N + t; j < a.big_dim; j += TPF) o[j] = 0;
+        if (t == 0) {
+            uint64_t bv = acc[(size_t)K * N];
+            if (a.mode == 0) o[a.big_dim] = bv; else o[a.big_dim] -= bv + a.body_const;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Plain transforms: one group of TPF threads per polynomial.  MODE 0: u64 (signed) input -> thread-major
 // spectrum scaled by 1/M (BSK conversion).  MODE 1: double input -> canonical order, unscaled (test hook).
 // ---------------------------------------------------------------------------------------------------
@@ -419,8 +588,40 @@ static int launch_pbs_t(const PbsArgs& a, int sm_count, cudaStream_t stream) {
     return check_launch("pbs_kernel");
 }
 
+template <int LOGN, int K, int LEVEL>
+static int launch_pbs8_t(const PbsArgs& a, int sm_count, cudaStream_t stream) {
+    using C = PbsCfg8<LOGN, K, LEVEL>;
+    const size_t smem = C::SMEM;
+    auto kern = pbs_kernel_v8<LOGN, K, LEVEL>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(pbs v8)");
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(pbs v8 carveout)");
+    int blocks_per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, C::TPF, smem);
+    if (e != cudaSuccess) return set_cuda_error(e, "occupancy(pbs v8)");
+    if (blocks_per_sm < 1) return set_error(TFX_ERR_UNSUPPORTED, "pbs v8: kernel does not fit on an SM");
+    if (getenv("TFX_PBS_VERBOSE")) fprintf(stderr, "[tfx] pbs_kernel_v8<%d,%d,%d>: %d CTAs/SM, %zu B smem\n", LOGN, K, LEVEL, blocks_per_sm, smem);
+    unsigned grid = (unsigned)sm_count * blocks_per_sm;
+    if (grid > a.count) grid = a.count;
+    if (const char* cap = getenv("TFX_PBS_GRID_CAP")) { unsigned g = (unsigned)atoi(cap); if (g && g < grid) grid = g; }
+    kern<<<grid, C::TPF, smem, stream>>>(a);
+    count_launch();
+    return check_launch("pbs_kernel_v8");
+}
+
+// v8 instantiations: the shipped sets and their neighbours; everything else runs the general kernel
+static bool pbs8_dispatch(const PbsLaunch& p, const PbsArgs& a, cudaStream_t stream, int* rc) {
+    if (p.base_log * p.level > 31 || getenv("TFX_PBS_V7")) return false;
+#define TFX_PBS8_CASE(LN, KK, LL) if (p.N == (1u << LN) && p.k == KK && p.level == LL) { *rc = launch_pbs8_t<LN, KK, LL>(a, p.sm_count, stream); return true; }
+    TFX_PBS8_CASE(10, 2, 1) TFX_PBS8_CASE(11, 1, 2) TFX_PBS8_CASE(11, 1, 1) TFX_PBS8_CASE(10, 1, 1) TFX_PBS8_CASE(10, 1, 2)
+    TFX_PBS8_CASE(9, 2, 1) TFX_PBS8_CASE(9, 1, 2)
+#undef TFX_PBS8_CASE
+    return false;
+}
+
 int pbs_supported(uint32_t N, uint32_t k) {
-    if (k == 1) return N == 512 || N == 1024 || N == 2048 || N == 4096;
+    if (k == 1) return N == 512 || N == 1024 || N == 2048 || N == 4096 || N == 8192;
     if (k == 2) return N == 512 || N == 1024 || N == 2048;
     return 0;
 }
@@ -437,8 +638,9 @@ int launch_pbs(const PbsLaunch& p, cudaStream_t stream) {
     }
     a.n = p.n; a.big_dim = p.big_dim; a.base_log = p.base_log; a.level = p.level; a.mode = p.mode; a.body_const = p.body_const;
     a.count = (uint32_t)p.count;
+    { int rc8 = 0; if (pbs8_dispatch(p, a, stream, &rc8)) return rc8; }
 #define TFX_PBS_CASE(LN, KK) if (p.N == (1u << LN) && p.k == KK) return launch_pbs_t<LN, KK>(a, p.sm_count, stream);
-    TFX_PBS_CASE(9, 1) TFX_PBS_CASE(10, 1) TFX_PBS_CASE(11, 1) TFX_PBS_CASE(12, 1)
+    TFX_PBS_CASE(9, 1) TFX_PBS_CASE(10, 1) TFX_PBS_CASE(11, 1) TFX_PBS_CASE(12, 1) TFX_PBS_CASE(13, 1)
     TFX_PBS_CASE(9, 2) TFX_PBS_CASE(10, 2) TFX_PBS_CASE(11, 2)
 #undef TFX_PBS_CASE
     return set_error(TFX_ERR_UNSUPPORTED, "pbs: no kernel compiled for this (N, k)");
@@ -483,6 +685,7 @@ int launch_fft(int which, uint32_t N, const void* in, void* out, const double* t
         case 1024: return launch_fft_t<10>(which, in, out, tw, polys, sm_count, stream);
         case 2048: return launch_fft_t<11>(which, in, out, tw, polys, sm_count, stream);
         case 4096: return launch_fft_t<12>(which, in, out, tw, polys, sm_count, stream);
+        case 8192: return launch_fft_t<13>(which, in, out, tw, polys, sm_count, stream);
         default: return set_error(TFX_ERR_UNSUPPORTED, "fft: unsupported N");
     }
 }

@@ -18,8 +18,11 @@ from typing import Iterable, List, Optional, Sequence, Tuple
 
 from .binding import PbsParams
 
-SUPPORTED_KN = {1: (512, 1024, 2048, 4096), 2: (512, 1024, 2048)}
-BIG_DIMS = (1024, 2048, 4096)   # candidate big LWE key dimensions (the table set is (k=1, N=big_dim)); smallest feasible wins
+SUPPORTED_KN = {1: (512, 1024, 2048, 4096, 8192), 2: (512, 1024, 2048)}
+# candidate big LWE key dimensions (the table set is (k=1, N=big_dim)); smallest feasible wins.  8192 is what 7-bit lookups need
+# (rounding_threshold_bits=7, the reference's ImageNet setting, run_homomorphic_eval.sh:25): the mod-switch noise at 2N = 8192
+# alone exceeds their budget.
+BIG_DIMS = (1024, 2048, 4096, 8192)
 
 
 def z_score(p_error: float) -> float:

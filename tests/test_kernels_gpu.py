@@ -15,6 +15,9 @@ TOY = [
     PbsParams(n=36, k=2, N=512, bsk_base_log=9, bsk_level=2, ksk_base_log=4, ksk_level=4, lwe_std=2.0**-30, glwe_std=2.0**-45),
     PbsParams(n=28, k=2, N=1024, bsk_base_log=10, bsk_level=3, ksk_base_log=6, ksk_level=2, lwe_std=2.0**-30, glwe_std=2.0**-50),
     PbsParams(n=20, k=2, N=2048, bsk_base_log=23, bsk_level=1, ksk_base_log=4, ksk_level=4, lwe_std=2.0**-30, glwe_std=2.0**-60),
+    # N = 8192: the polynomial size 7-bit lookups need (rounding_threshold_bits=7); general kernel, twiddles in global memory
+    PbsParams(n=10, k=1, N=8192, bsk_base_log=20, bsk_level=1, ksk_base_log=4, ksk_level=3, lwe_std=2.0**-30, glwe_std=2.0**-60),
+    PbsParams(n=8, k=1, N=8192, bsk_base_log=14, bsk_level=2, ksk_base_log=4, ksk_level=3, lwe_std=2.0**-30, glwe_std=2.0**-60),
 ]
 IDS = [f"N{p.N}k{p.k}l{p.bsk_level}" for p in TOY]
 
@@ -29,7 +32,7 @@ def oracle_keys(O, p: PbsParams, seed, set_id=0):
 
 def test_fft_forward_inverse_parity(gpu_ctx, oracle):
     rng = np.random.default_rng(1)
-    for N in (512, 1024, 2048, 4096):
+    for N in (512, 1024, 2048, 4096, 8192):
         polys = rng.integers(-2**20, 2**20, size=(5, N)).astype(np.float64)
         polys[1] = rng.integers(-2**62, 2**62, size=N).astype(np.float64)
         d = torch.from_numpy(polys).to(gpu_ctx.device)
