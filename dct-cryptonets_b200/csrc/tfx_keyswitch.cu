@@ -290,6 +290,10 @@ static int launch_keyswitch_imma(const KsLaunch& p, cudaStream_t stream) {
     {   // per launch: the attribute is per device, and a process may drive several devices / host threads
         cudaError_t e = cudaFuncSetAttribute(keyswitch_imma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(keyswitch_imma)");
+        // same shared-memory carve-out as the PBS kernels: the chains of a lookup layer run on several streams, and an SM only
+        // hosts CTAs of kernels that agree on the L1 / shared-memory split (a different split waits for the SM to drain)
+        cudaFuncSetAttribute(keyswitch_imma_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(ks_decompose_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
     ks_decompose_kernel<<<(unsigned)p.sm_count * 16, 256, 0, stream>>>(p.in, p.digits, (uint32_t)p.count, p.big_dim, p.base_log, p.level, p.shift);
     count_launch();

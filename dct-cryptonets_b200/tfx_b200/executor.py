@@ -112,15 +112,18 @@ class CircuitExecutor:
         self._bit_luts: Dict[Tuple[int, int], Tuple[torch.Tensor, int]] = {}
         self._weights: Dict[int, torch.Tensor] = {}
         self._bias: Dict[int, torch.Tensor] = {}
-        # Two-stream lookup layers: a rank's share of a layer is split in two halves whose rounding chains are enqueued on
-        # two streams, so the second half's CTAs fill the SMs that the first half's last, partial wave leaves idle (and
-        # vice versa).  With W ranks a layer of 12 288 ciphertexts leaves 12 288 / W per kernel — a few waves only — and
-        # every one of the ~8 kernels of a chain would otherwise pay its own tail.  On by default for world_size > 1;
-        # TFX_SPLIT_STREAMS=0/1 overrides.  Results are identical (the halves are independent ciphertexts).
+        # Wave-sized chains on several streams: with W ranks a layer of 12 288 ciphertexts leaves 12 288 / W per kernel — 2.6
+        # waves of the bit-extraction PBS at W = 8 — and every one of the ~14 launches of a rounding chain would pay its own
+        # partial last wave.  A rank's share of a layer is therefore cut into chunks of whole waves (WAVE_ROWS ciphertexts = the
+        # resident grid of the bit kernel = two waves of the table kernel) whose chains are enqueued on separate streams: when
+        # one chunk's kernel runs out of ciphertexts the next step of another chunk is already queued and takes the freed SMs,
+        # so only the end of the layer sees idle SMs.  On by default for world_size > 1; TFX_SPLIT_STREAMS=0 switches it off,
+        # TFX_SPLIT_STREAMS=k (k >= 2) allows up to k concurrent chains.  Results are identical (the chunks are independent
+        # ciphertexts).
         env = os.environ.get("TFX_SPLIT_STREAMS")
-        self.split_streams = (world_size > 1) if env is None else (env == "1")
-        self._side_stream: Optional[torch.cuda.Stream] = None
-        self._side_ctx: Optional[Context] = None
+        self.max_chains = (4 if world_size > 1 else 1) if env is None else max(1, int(env) if env != "1" else 2)
+        self.split_streams = self.max_chains > 1
+        self._sides: List[Tuple[torch.cuda.Stream, Context]] = []
         self._perm: Dict[Tuple[int, int, int], Tuple[torch.Tensor, np.ndarray]] = {}
         self._prepare_constants()
 
@@ -240,12 +243,29 @@ class CircuitExecutor:
             self._perm[key] = (torch.from_numpy(perm).to(self.ctx.device), order)
         return self._perm[key]
 
-    def _side(self) -> Tuple[torch.cuda.Stream, Context]:
-        if self._side_ctx is None:
-            self._side_stream = torch.cuda.Stream(self.ctx.device)
-            with torch.cuda.stream(self._side_stream):
-                self._side_ctx = Context(self.ctx.device.index)      # binds to the side stream; own scratch + hand-out counter
-        return self._side_stream, self._side_ctx
+    WAVE_ROWS = 592          # 148 SMs x 4 resident CTAs of the bit-extraction PBS kernel (2 waves of the table kernel)
+
+    def _side(self, i: int) -> Tuple[torch.cuda.Stream, Context]:
+        while len(self._sides) <= i:
+            st = torch.cuda.Stream(self.ctx.device)
+            with torch.cuda.stream(st):
+                self._sides.append((st, Context(self.ctx.device.index)))   # binds to the side stream; own scratch + hand-out counter
+        return self._sides[i]
+
+    def _chunks(self, nloc: int) -> List[Tuple[int, int]]:
+        """row ranges of the concurrent chains: whole waves per chunk, at most max_chains chunks"""
+        if self.max_chains <= 1 or nloc <= self.WAVE_ROWS:
+            return [(0, nloc)]
+        mode = os.environ.get("TFX_CHUNK_MODE", "wave")
+        if mode == "equal":
+            per = -(-nloc // self.max_chains)
+            return [(r0, min(nloc, r0 + per)) for r0 in range(0, nloc, per)]
+        waves = -(-nloc // self.WAVE_ROWS)
+        per = -(-waves // self.max_chains) * self.WAVE_ROWS
+        if mode == "small_first":                        # the partial chunk leads, whole-wave chunks finish the layer
+            first = nloc % per or per
+            return [(0, first)] + [(r0, r0 + per) for r0 in range(first, nloc, per)]
+        return [(r0, min(nloc, r0 + per)) for r0 in range(0, nloc, per)]
 
     def _gather(self, local: torch.Tensor, C: int, per: int, hw: int) -> torch.Tensor:
         return gather_channels(local, C, per, hw, self.world, self.pg)
@@ -358,16 +378,17 @@ class CircuitExecutor:
                                 c0 = c1
                     n_small = self.params[TLU_SET].n + 1
 
-                    def chain(c_, r0, r1):
-                        """rounding chain + table lookup of rows [r0, r1) of this rank's share, enqueued on c_'s stream"""
-                        for b, nb in enumerate(steps):
-                            e_ = min(r1, nb)
-                            if e_ <= r0:
-                                break
-                            a_, n_ = src[r0:e_], e_ - r0
-                            small = timed("ks_bit", n_, lambda: keys.keyswitch(BIT_SET, a_, shift=w - b, body_offset=1 << 62, ctx=c_))
-                            lut, c = self._bit_luts[(w, b)]
-                            timed("pbs_bit", n_, lambda: keys.pbs(BIT_SET, small, lut, self._zero_idx[:n_], mode=1, body_const=c, out=a_, ctx=c_))
+                    def bit_step(c_, r0, r1, b):
+                        """extraction step b of rows [r0, r1) of this rank's share (only the rows still active), on c_'s stream"""
+                        e_ = min(r1, steps[b])
+                        if e_ <= r0:
+                            return
+                        a_, n_ = src[r0:e_], e_ - r0
+                        small = timed("ks_bit", n_, lambda: keys.keyswitch(BIT_SET, a_, shift=w - b, body_offset=1 << 62, ctx=c_))
+                        lut, c = self._bit_luts[(w, b)]
+                        timed("pbs_bit", n_, lambda: keys.pbs(BIT_SET, small, lut, self._zero_idx[:n_], mode=1, body_const=c, out=a_, ctx=c_))
+
+                    def lookup_step(c_, r0, r1):
                         small = c_.empty_u64(r1 - r0, n_small)
                         for s0, s1, wv in segments:                                # one keyswitch per width: the ciphertext is scaled by 2^(w - wv)
                             g0, g1 = max(s0, r0), min(s1, r1)
@@ -375,17 +396,28 @@ class CircuitExecutor:
                                 timed("ks_tlu", g1 - g0, lambda: keys.keyswitch(TLU_SET, src[g0:g1], shift=w - wv, out=small[g0 - r0: g1 - r0], ctx=c_))
                         timed("pbs_tlu", r1 - r0, lambda: keys.pbs(TLU_SET, small, self._luts[op.dst], idx_rows[r0:r1], out=out[r0:r1], ctx=c_))
 
-                    if self.split_streams and nloc >= 2:
-                        side, side_ctx = self._side()
+                    chunks = self._chunks(nloc)
+                    if len(chunks) > 1:
+                        # one stream per chunk; the steps are enqueued round-robin over the chunks so that the chains advance
+                        # together (the GPU serves older grids first): a chunk's partial last wave is filled by the next chunk's
+                        # CTAs of the same step, and the first chunk's next step is queued by the time the last chunk drains
                         main = torch.cuda.current_stream(ctx.device)
-                        half = nloc // 2
-                        side.wait_stream(main)                       # acc / out are produced / allocated on the main stream
-                        chain(ctx, 0, half)
-                        with torch.cuda.stream(side):
-                            chain(side_ctx, half, nloc)
-                        main.wait_stream(side)
+                        lanes = [(main, ctx)] + [self._side(i) for i in range(len(chunks) - 1)]
+                        for st, _ in lanes[1:]:
+                            st.wait_stream(main)                     # acc / out are produced / allocated on the main stream
+                        for b in range(len(steps)):
+                            for (st, sctx), (r0, r1) in zip(lanes, chunks):
+                                with torch.cuda.stream(st):
+                                    bit_step(sctx, r0, r1, b)
+                        for (st, sctx), (r0, r1) in zip(lanes, chunks):
+                            with torch.cuda.stream(st):
+                                lookup_step(sctx, r0, r1)
+                        for st, _ in lanes[1:]:
+                            main.wait_stream(st)
                     else:
-                        chain(ctx, 0, nloc)
+                        for b in range(len(steps)):
+                            bit_step(ctx, 0, nloc, b)
+                        lookup_step(ctx, 0, nloc)
                     if not uniform:                                  # back to channel order: out[perm[i]] = sorted_out[i]
                         unsorted = torch.empty_like(out)
                         unsorted.index_copy_(0, perm_d, out)
@@ -395,7 +427,9 @@ class CircuitExecutor:
                 else:
                     out = ctx.empty_u64(0, words)
                 del acc
-                vals[op.dst] = self._gather(out, C, per, H * W).view(C, H, W, words)
+                # layer exchange (NCCL all-gather on the compute stream); timed as class 'gather' when profiling
+                vals[op.dst] = (timed("gather", nloc, lambda: self._gather(out, C, per, H * W)) if self.world > 1
+                                else self._gather(out, C, per, H * W)).view(C, H, W, words)
             if time_layers:
                 ev1 = torch.cuda.Event(enable_timing=True); ev1.record()
                 layer_t.append((op.name, ev0, ev1))

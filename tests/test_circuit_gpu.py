@@ -87,19 +87,20 @@ def test_per_channel_widths_match_oracle_and_clear(gpu_ctx, oracle):
     clear = C.evaluate_clear(circ, q_in[None])[0]
     assert np.array_equal(CO.decrypt_output(circ, keys, ref).reshape(clear.shape), clear)
     assert stats.pbs_bit == circ.pbs_count()["bit"]
-    ex.split_streams = True
+    ex.max_chains, ex.WAVE_ROWS = 3, 8                       # concurrent wave-sized chains forced on (toy wave size)
     assert np.array_equal(gpu_ctx.to_host_u64(ex.run(cts)), ref)
 
 
 def test_two_stream_lookup_layers_give_identical_ciphertexts(gpu_ctx):
-    """the multi-GPU executor splits a rank's share of every lookup layer over two streams (executor.py); forced on here
-    on one GPU: every output word must equal the single-stream run, repeatedly (a race would show up as a difference)"""
+    """the multi-GPU executor cuts a rank's share of every lookup layer into wave-sized chunks whose chains run on several
+    streams (executor.py); forced on here on one GPU with a toy wave size: every output word must equal the single-stream
+    run, repeatedly (a race would show up as a difference)"""
     model, calib, circ = build(seed=2)
     one = CircuitExecutor(circ, (TOY_TLU, TOY_BIT), ctx=gpu_ctx, input_std=2.0**-50)
-    one.split_streams = False
+    one.max_chains = 1
     one.keygen(seed=7)
     two = CircuitExecutor(circ, (TOY_TLU, TOY_BIT), ctx=gpu_ctx, input_std=2.0**-50)
-    two.split_streams = True
+    two.max_chains, two.WAVE_ROWS = 4, 8
     two.use_keys(one.keys)
     for img in range(3):
         q_in = C.quantize_input(circ, calib[img:img + 1].numpy())[0]
@@ -107,7 +108,7 @@ def test_two_stream_lookup_layers_give_identical_ciphertexts(gpu_ctx):
         want = gpu_ctx.to_host_u64(one.run(cts))
         for _ in range(2):
             assert np.array_equal(gpu_ctx.to_host_u64(two.run(cts)), want)
-    assert two._side_ctx is not None and one._side_ctx is None
+    assert len(two._sides) >= 2 and not one._sides
 
 
 def test_qat_circuit_executes_like_the_clear_evaluator(gpu_ctx):

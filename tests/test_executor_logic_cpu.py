@@ -113,7 +113,7 @@ def test_executor_host_logic_equals_oracle_circuit(oracle, mode):
         outs = []
         for rank in range(world):
             ex = CircuitExecutor(circ, (TLU, BIT), ctx=FakeContext(oracle), rank=rank, world_size=world, input_std=2.0**-50)
-            ex.split_streams = False
+            ex.max_chains = 1
             ex.use_keys(FakeKeys(oracle, okeys, (TLU, BIT)))
             if world > 1:                                    # stand-in for the all-gather: every rank's block, computed here in turn
                 ex._gather = None

@@ -1,5 +1,5 @@
-"""Opt-in features that have not had a GPU run yet.  Kept in a file that sorts last and marked xfail(strict=False): a failure here
-cannot mask, or disturb the CUDA context of, the parity suite proper."""
+"""Opt-in circuit variants (not the default layout): they must stay word-for-word equal to the oracle like everything else.
+(Round 1 shipped this test as xfail(strict=False) before its first GPU run; it passed on the B200 and is strict now.)"""
 import numpy as np
 import pytest
 import torch
@@ -13,8 +13,6 @@ from test_circuit_gpu import TOY_BIT, TOY_TLU
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.xfail(strict=False, reason="fuse_residual is opt-in and was validated against the oracle on the CPU only "
-                                        "(tests/test_executor_logic_cpu.py[fused_widths]); first GPU run pending")
 def test_fused_residual_lookups_match_oracle_and_clear(gpu_ctx, oracle):
     """opt-in fused residual lookups (circuit.FusedAddOp): GPU ciphertexts == oracle circuit word for word, decrypted == clear"""
     from oracle import circuit_oracle as CO
