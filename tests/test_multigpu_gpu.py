@@ -37,7 +37,17 @@ def _worker(rank, world, port, ret):
         multi = CircuitExecutor(circ, (tlu, bit), ctx=ctx, rank=rank, world_size=world, process_group=dist.group.WORLD, input_std=2.0**-50)
         multi.use_keys(single.keys)
         got = ctx.to_host_u64(multi.run(cts))
-        ret[rank] = bool(np.array_equal(got, want))
+        ok = bool(np.array_equal(got, want))
+        # default seeds come from the OS CSPRNG: rank 0 draws, every rank must end up with the same keys and the same input ciphertexts
+        multi.keygen()
+        import hashlib
+        digest = hashlib.sha256(multi.keys.get_secret(-1).tobytes() + ctx.to_host_u64(multi.encrypt(q)).tobytes()).hexdigest()
+        all_d = [None] * world
+        dist.all_gather_object(all_d, digest)
+        fresh = CircuitExecutor(circ, (tlu, bit), ctx=ctx, input_std=2.0**-50)
+        fresh.keygen()
+        ok = ok and len(set(all_d)) == 1 and not np.array_equal(fresh.keys.get_secret(-1), multi.keys.get_secret(-1))
+        ret[rank] = ok
     finally:
         dist.destroy_process_group()
 

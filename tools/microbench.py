@@ -2,6 +2,8 @@
 
 python tools/microbench.py [--batches 148,1184,...] [--sets tlu,bit] [--json out.json]
 Times each kernel with CUDA events on the launching stream (3 warm-ups, inputs larger than L2 or L2 flushed).
+Under torch.distributed.run (N ranks, one per GPU) a batch of B ciphertexts is sharded B/N per rank — keys replicated, no
+data-path collective — and the reported rates are whole-job (B over the slowest rank's time).
 """
 import argparse
 import json
@@ -61,35 +63,62 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--no-ks", action="store_true")
     args = ap.parse_args()
-    ctx = Context(0)
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = Context(local)
     names = args.sets.split(",")
     sets = [DEFAULT_SETS[n] for n in names]
     keys = KeySet.generate(ctx, sets, 1)
     dfma = ctx.probe_rate(0)
     imac = ctx.probe_rate(1)
-    print(f"measured DFMA peak {dfma / 1e12:.2f} TFLOP/s, u64 MAC peak {imac / 1e12:.2f} TMAC/s", flush=True)
+    if rank == 0:
+        print(f"measured DFMA peak {dfma / 1e12:.2f} TFLOP/s, u64 MAC peak {imac / 1e12:.2f} TMAC/s", flush=True)
+
+    def slowest(t):
+        if world == 1:
+            return t
+        v = torch.tensor([t], dtype=torch.float64, device=ctx.device)
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        return float(v.item())
+
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.int32, device=ctx.device)     # 256 MB > L2
     rows = []
-    for B in [int(b) for b in args.batches.split(",")]:
+    for Btot in [int(b) for b in args.batches.split(",")]:
+        B = Btot // world + (1 if rank < Btot % world else 0)          # this rank's shard
         for sid, (name, p) in enumerate(zip(names, sets)):
-            g = torch.Generator(device="cuda"); g.manual_seed(B)
+            if B == 0:                                   # fewer ciphertexts than ranks: this rank idles
+                t_pbs = slowest(0.0)
+                if not args.no_ks:
+                    slowest(0.0)
+                continue
+            g = torch.Generator(device="cuda"); g.manual_seed(Btot * 131 + rank)
             big = torch.randint(-2**62, 2**62, (B, keys.big_dim + 1), dtype=torch.int64, device=ctx.device, generator=g)
             small = torch.randint(-2**62, 2**62, (B, p.n + 1), dtype=torch.int64, device=ctx.device, generator=g)
             luts = torch.randint(-2**62, 2**62, (4, p.N), dtype=torch.int64, device=ctx.device, generator=g)
             idx = torch.zeros(B, dtype=torch.int32, device=ctx.device)
             out = ctx.empty_u64(B, keys.big_dim + 1)
             ks_out = ctx.empty_u64(B, p.n + 1)
-            t_pbs = time_fn(lambda: keys.pbs(sid, small, luts, idx, out=out), args.warmup, args.iters, flush)
-            row = {"set": name, "B": B, "pbs_s": t_pbs, "pbs_per_s": B / t_pbs,
-                   "pbs_tflops": B * P.pbs_flops(p) / t_pbs / 1e12, "pbs_frac_dfma": B * P.pbs_flops(p) / t_pbs / dfma,
-                   "bsk_GBps_algorithmic": P.bsk_bytes(p) / t_pbs / 1e9}
+            t_pbs = slowest(time_fn(lambda: keys.pbs(sid, small, luts, idx, out=out), args.warmup, args.iters, flush))
+            row = {"set": name, "B": Btot, "n_gpus": world, "pbs_s": t_pbs, "pbs_per_s": Btot / t_pbs, "pbs_per_s_per_gpu": Btot / t_pbs / world,
+                   "pbs_tflops": Btot * P.pbs_flops(p) / t_pbs / 1e12, "pbs_frac_dfma": Btot * P.pbs_flops(p) / t_pbs / dfma / world,
+                   "latency_ms": t_pbs * 1e3,
+                   "bsk_GBps_algorithmic": P.bsk_bytes(p) / t_pbs / 1e9,
+                   "pbs_roofline": "min(key bytes at HBM rate, flops at DFMA peak)",
+                   "pbs_roofline_frac": (max(P.bsk_bytes(p) / 6551.7e9, -(-Btot // world) * P.pbs_flops(p) / dfma)) / t_pbs}
             if not args.no_ks:
-                t_ks = time_fn(lambda: keys.keyswitch(sid, big, out=ks_out), args.warmup, args.iters, flush)
+                t_ks = slowest(time_fn(lambda: keys.keyswitch(sid, big, out=ks_out), args.warmup, args.iters, flush))
                 macs = P.ks_macs(p, keys.big_dim)
-                row.update({"ks_s": t_ks, "ks_per_s": B / t_ks, "ks_tmacs": B * macs / t_ks / 1e12, "ks_frac_imac": B * macs / t_ks / imac})
+                row.update({"ks_s": t_ks, "ks_per_s": Btot / t_ks, "ks_tmacs": Btot * macs / t_ks / 1e12, "ks_frac_imac": Btot * macs / t_ks / imac / world})
             rows.append(row)
-            print(json.dumps(row), flush=True)
-    if args.json:
+            if rank == 0:
+                print(json.dumps(row), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    if args.json and rank == 0:
         with open(args.json, "w") as f:
             json.dump({"dfma_peak": dfma, "imac_peak": imac, "rows": rows}, f, indent=1)
 

@@ -60,6 +60,7 @@ def main() -> None:
     ap.add_argument("--synthetic-cifar", type=int, default=200, metavar="N", help="write N synthetic CIFAR-10 images (0: use what is in workdir)")
     ap.add_argument("script_args", nargs=argparse.REMAINDER)
     args = ap.parse_args()
+    args.reference = os.path.abspath(args.reference)                   # the script runs from <workdir>
     script = os.path.join(args.reference, "homomorphic_eval.py")
     if not os.path.isfile(script):
         raise SystemExit(f"{script} not found (the reference tree is only present in the build container)")
