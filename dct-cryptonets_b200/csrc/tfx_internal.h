@@ -31,6 +31,10 @@ struct KsLaunch {
     uint32_t big_dim, n; int base_log, level; uint32_t shift; uint64_t body_offset; size_t count; int sm_count;
 };
 int launch_keyswitch(const KsLaunch& p, cudaStream_t stream);
+uint32_t ksk_npad(uint32_t n);
+// tcgen05 / TMA variant of the limb-split contraction (tfx_keyswitch_umma.cu); digits and key bytes as for the IMMA kernel
+bool keyswitch_umma_ok(uint32_t big_dim, uint32_t n, int level);
+int launch_keyswitch_umma(const KsLaunch& p, cudaStream_t stream);
 
 // keygen / client kernels (tfx_keygen.cu)
 int launch_gen_binary_key(const uint8_t seed[16], int purpose, uint32_t set, uint32_t dim, uint64_t* key_d, cudaStream_t s);

@@ -298,6 +298,8 @@ static int launch_keyswitch_imma(const KsLaunch& p, cudaStream_t stream) {
     ks_decompose_kernel<<<(unsigned)p.sm_count * 16, 256, 0, stream>>>(p.in, p.digits, (uint32_t)p.count, p.big_dim, p.base_log, p.level, p.shift);
     count_launch();
     int rc = check_launch("ks_decompose_kernel"); if (rc) return rc;
+    // Blackwell tensor path (tcgen05.mma kind::i8, TMA operands, TMEM accumulators); TFX_KS_IMMA=1 keeps the mma.sync kernel
+    if (keyswitch_umma_ok(p.big_dim, p.n, p.level)) return launch_keyswitch_umma(p, stream);
     KiArgs a;
     a.dig = p.digits; a.kb = p.ksk_bytes; a.corr = p.ksk + (size_t)p.big_dim * p.level * npad; a.in = p.in; a.out = p.out;
     a.big_dim = p.big_dim; a.n = p.n; a.Kp = Kp; a.kc = kc; a.shift = p.shift; a.body_offset = p.body_offset; a.count = (uint32_t)p.count;
