@@ -121,3 +121,45 @@ def test_unmodified_reference_script_runs_to_keygen(tmp_path):
         assert r.returncode == 0 and "Done" in log, log[-2000:]
     else:
         assert r.returncode != 0 and "keygen" in log and "no CPU fallback" in log, log[-2000:]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+def test_reference_checkpoint_format_loads_and_changes_the_circuit(tmp_path):
+    """A checkpoint in the reference's own container format (train.py:83-89: {'epoch', 'state' = DataParallel state dict, 'prec1',
+    'prec5', 'optimizer'}) is picked up by the unmodified driver (homomorphic_eval.py:247-253) and its weights — not the random
+    initialisation — are what gets compiled: the circuit text written to mlir.txt differs from the no-checkpoint run.
+    (Brevitas itself is not installable here: parameter names are those of compat/brevitas, see DESIGN.md.)"""
+    pkg = os.path.join(ROOT, "dct-cryptonets_b200")
+    ckpt = tmp_path / "best.tar"
+    make = f"""
+import os, sys, torch, torch.nn as nn
+sys.path.insert(0, {REF!r}); sys.path.insert(0, {pkg!r}); sys.path.append({os.path.join(pkg, "compat")!r})
+os.environ["BREVITAS_IGNORE_MISSING_KEYS"] = "1"
+from io_utils import model_dict
+from utils import BaselineTrain
+torch.manual_seed(7)
+model = nn.DataParallel(BaselineTrain(model_dict["ResNet20qat"](bit_width=4, in_channels=24, img_size=16), 10))
+with torch.no_grad():
+    for p_ in model.parameters():
+        p_.add_(0.05 * torch.randn_like(p_))          # "trained": anything but the seeded initialisation
+torch.save({{"epoch": 3, "state": model.state_dict(), "prec1": 91.25, "prec5": 99.5, "optimizer": {{}}}}, {str(ckpt)!r})
+"""
+    r = subprocess.run([sys.executable, "-c", make], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and ckpt.exists(), r.stderr[-2000:]
+    texts = {}
+    for tag, extra in (("ckpt", ["--checkpoint_path", str(ckpt)]), ("none", [])):
+        wd = tmp_path / tag
+        cmd = [sys.executable, os.path.join(ROOT, "tools", "run_reference_eval.py"), "--workdir", str(wd), "--synthetic-cifar", "120", "--",
+               "--dataset", "cifar10", "--model", "ResNet20qat", "--dct_status", "--channels", "24", "--filter_size", "4", "--image_size_dct", "16",
+               "--bit_width", "4", "--fhe_mode", "simulate", "--calib_batch_size", "100", "--test_batch_size", "2", "--test_subset", "2",
+               "--rounding_threshold_bits", "6", "--n_bits", "5", "--p_error", "0.01"] + extra
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+        log = r.stdout + r.stderr
+        assert "Time for FHE compilation" in log, log[-2000:]
+        if tag == "ckpt":
+            assert "Loaded checkpoint" in log and "91.250% Top-1 Acc. @ epoch 3" in log and "No checkpoint loaded" not in log, log[-2000:]
+        else:
+            assert "No checkpoint loaded" in log
+        texts[tag] = open(wd / "mlir.txt").read()
+    assert texts["ckpt"] != texts["none"]
+
