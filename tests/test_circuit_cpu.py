@@ -166,7 +166,10 @@ def test_parameter_picker_meets_noise_constraints(tiny):
     spec2 = circ.noise_spec(); spec2.p_error = 1e-3
     tlu2, bit2, _ = P.pick_parameters(spec2)
     assert P._cost(spec2, tlu2, bit2) >= P._cost(spec, tlu, bit) and P._check(spec2, tlu2, bit2, P.z_score(1e-3))[0]
+    # (N = 8192 made p_error = 1e-30 reachable for this small circuit; 11-bit lookups are beyond every supported polynomial size)
     spec3 = circ.noise_spec(); spec3.p_error = 1e-30
+    for lk in spec3.lookups:
+        lk.acc_bits, lk.keep_bits = max(lk.acc_bits, 12), 11
     with pytest.raises(ValueError):
         P.pick_parameters(spec3)
 
