@@ -64,7 +64,7 @@ static int pass_plan(int logM, int wd[8]) {
     switch (logM) {
         case 8: wd[0] = 3; wd[1] = 3; wd[2] = 2; return 3;
         case 9: wd[0] = 3; wd[1] = 3; wd[2] = 3; return 3;
-        case 10: wd[0] = 3; wd[1] = 2; wd[2] = 3; wd[3] = 2; return 4;
+        case 10: wd[0] = 2; wd[1] = 2; wd[2] = 3; wd[3] = 3; return 4;
         case 11: wd[0] = 3; wd[1] = 3; wd[2] = 3; wd[3] = 2; return 4;
         case 12: wd[0] = 3; wd[1] = 3; wd[2] = 3; wd[3] = 3; return 4;
         default: { int n = 0, left = logM; while (left >= 3) { wd[n++] = 3; left -= 3; } if (left) wd[n++] = left; return n; }

@@ -168,7 +168,7 @@ __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_doub
 template <int LOGM> struct FftPlan;
 template <> struct FftPlan<8>  { static constexpr int P = 3; static constexpr int WD[4] = {3, 3, 2, 0}; };
 template <> struct FftPlan<9>  { static constexpr int P = 3; static constexpr int WD[4] = {3, 3, 3, 0}; };
-template <> struct FftPlan<10> { static constexpr int P = 4; static constexpr int WD[4] = {3, 2, 3, 2}; };
+template <> struct FftPlan<10> { static constexpr int P = 4; static constexpr int WD[4] = {2, 2, 3, 3}; };   // the two radix-4 levels fuse into one 16-point pass (pbs_kernel_v8)
 template <> struct FftPlan<11> { static constexpr int P = 4; static constexpr int WD[4] = {3, 3, 3, 2}; };
 template <> struct FftPlan<12> { static constexpr int P = 4; static constexpr int WD[4] = {3, 3, 3, 3}; };
 
@@ -432,6 +432,45 @@ __device__ __forceinline__ void fft_forward_multi(double2 (&x)[NT][8], double2 (
     }
 }
 
+// forward tail for the fused plan: the caller ran passes 0 and 1 (fused16_forward), stored every transform at its natural
+// index and passed a CTA barrier; this runs passes 2.. on all NT transforms interleaved
+template <int LOGM, int NT, typename SYNC_WARP>
+__device__ __forceinline__ void fft_forward_multi_from2(double2 (&x)[NT][8], double2 (&w)[7], int t, double2* __restrict__ bufs,
+                                                        const double2* __restrict__ tw, SYNC_WARP wsync) {
+    using PL = FftPlan<LOGM>;
+    constexpr int M = 1 << LOGM;
+    static_assert(PL::P == 4, "fused plan has four passes");
+    load_tw<LOGM, 2>(w, t, tw);
+#pragma unroll
+    for (int q = 0; q < NT; q++) pass_load<LOGM, 2>(x[q], t, bufs + q * M);
+#pragma unroll
+    for (int q = 0; q < NT; q++) pass_nodes<LOGM, 2, false>(x[q], w);
+#pragma unroll
+    for (int q = 0; q < NT; q++) pass_store<LOGM, 2>(x[q], t, bufs + q * M);
+    load_tw<LOGM, 3>(w, t, tw);
+    wsync();
+#pragma unroll
+    for (int q = 0; q < NT; q++) pass_load<LOGM, 3>(x[q], t, bufs + q * M);
+#pragma unroll
+    for (int q = 0; q < NT; q++) pass_nodes<LOGM, 3, false>(x[q], w);
+}
+
+// inverse counterpart: runs pass 2 on all NT spectra (stored by the caller with pass_store<LOGM, 3>) and stores them; the caller
+// then passes a CTA barrier and finishes with fused16_inverse
+template <int LOGM, int NT, typename SYNC_WARP>
+__device__ __forceinline__ void fft_inverse_multi_pass2(int t, double2* __restrict__ bufs, const double2* __restrict__ tw, SYNC_WARP wsync) {
+    constexpr int M = 1 << LOGM;
+    double2 y[NT][8], w[7];
+    load_tw<LOGM, 2>(w, t, tw);
+    wsync();
+#pragma unroll
+    for (int q = 0; q < NT; q++) pass_load<LOGM, 2>(y[q], t, bufs + q * M);
+#pragma unroll
+    for (int q = 0; q < NT; q++) pass_nodes<LOGM, 2, true>(y[q], w);
+#pragma unroll
+    for (int q = 0; q < NT; q++) pass_store<LOGM, 2>(y[q], t, bufs + q * M);
+}
+
 // inverse, all passes BELOW the last one: the caller has run the last pass's nodes on every spectrum and stored it with
 // pass_store<LOGM, LAST> into bufs + q*M (lane-private positions).  On return y[q][e] = coefficient pair t + e*TPF (no 1/M).
 template <int LOGM, int NT, typename SYNC_CTA, typename SYNC_WARP>
@@ -464,6 +503,57 @@ __device__ __forceinline__ void fft_inverse_multi_rest(double2 (&y)[NT][8], int 
     for (int q = 0; q < NT; q++) pass_load<LOGM, 0>(y[q], t, bufs + q * M);
 #pragma unroll
     for (int q = 0; q < NT; q++) pass_nodes<LOGM, 0, true>(y[q], w);
+}
+
+// ---- M = 1024, plan {2,2,3,3}: the two radix-4 levels of the plan fused into ONE 16-point pass per thread (no exchange
+// between them).  A thread of a 64-thread group holds z[e] = point tl + 64 e (e = 0..15) of its transform: level 0 nodes are
+// {q, q+4, q+8, q+12} (stride 256, node 0), level 1 nodes are {4h .. 4h+3} (stride 64, node h = top two index bits).  The
+// arithmetic per node is node_forward<2,.> / node_inverse<2,.> exactly (same order of operations, same twiddle entries).
+__device__ __forceinline__ void r4_forward(double2& y0, double2& y1, double2& y2, double2& y3, double2 w1, double2 w2, double2 w3) {
+    y1 = cmul(y1, w1); y2 = cmul(y2, w2); y3 = cmul(y3, w3);
+    { const double2 a = y0, b = y2, d = csub(a, b); y0 = cadd(a, b); y2 = d; }
+    { const double2 a = y1, b = y3, d = csub(a, b); y1 = cadd(a, b); y3 = mul_i(d); }
+    { const double2 a = y0, b = y1; y0 = cadd(a, b); y1 = csub(a, b); }
+    { const double2 a = y2, b = y3; y2 = cadd(a, b); y3 = csub(a, b); }
+}
+__device__ __forceinline__ void r4_inverse(double2& y0, double2& y1, double2& y2, double2& y3, double2 w1, double2 w2, double2 w3) {
+    { const double2 a = y0, b = y1; y0 = cadd(a, b); y1 = csub(a, b); }
+    { const double2 a = y2, b = y3; y2 = cadd(a, b); y3 = csub(a, b); }
+    { const double2 a = y0, b = y2; y0 = cadd(a, b); y2 = csub(a, b); }
+    { const double2 a = y1, b = mul_mi(y3); y1 = cadd(a, b); y3 = csub(a, b); }
+    y1 = cmulc(y1, w1); y2 = cmulc(y2, w2); y3 = cmulc(y3, w3);
+}
+// tw: the flat node-twiddle table of M = 1024 (pass 0 at offset 0: node 0; pass 1 at offset 3: nodes 0..3, three entries each)
+__device__ __forceinline__ void fused16_forward(double2 (&z)[16], const double2* __restrict__ tw) {
+    {
+        const double2 w1 = tw[0], w2 = tw[1], w3 = tw[2];
+#pragma unroll
+        for (int q = 0; q < 4; q++) r4_forward(z[q], z[q + 4], z[q + 8], z[q + 12], w1, w2, w3);
+    }
+#pragma unroll
+    for (int h = 0; h < 4; h++) {
+        const double2 w1 = tw[3 + 3 * h], w2 = tw[4 + 3 * h], w3 = tw[5 + 3 * h];
+        r4_forward(z[4 * h], z[4 * h + 1], z[4 * h + 2], z[4 * h + 3], w1, w2, w3);
+    }
+}
+__device__ __forceinline__ void fused16_inverse(double2 (&z)[16], const double2* __restrict__ tw) {
+#pragma unroll
+    for (int h = 0; h < 4; h++) {
+        const double2 w1 = tw[3 + 3 * h], w2 = tw[4 + 3 * h], w3 = tw[5 + 3 * h];
+        r4_inverse(z[4 * h], z[4 * h + 1], z[4 * h + 2], z[4 * h + 3], w1, w2, w3);
+    }
+    {
+        const double2 w1 = tw[0], w2 = tw[1], w3 = tw[2];
+#pragma unroll
+        for (int q = 0; q < 4; q++) r4_inverse(z[q], z[q + 4], z[q + 8], z[q + 12], w1, w2, w3);
+    }
+}
+
+// coefficient-pair index (j, j + M) that element e of thread t holds before the first forward pass / after the last inverse pass
+// (t + e * TPF when the first pass is a radix-8 pass; a leading radix-4 pass places its two nodes per thread differently)
+template <int LOGM>
+__device__ __forceinline__ int first_pass_index(int t, int e) {
+    return elem_index<LOGM, PassInfo<LOGM, 0>::LO, PassInfo<LOGM, 0>::WD>(t, e);
 }
 
 // canonical transform position of element e of thread t after the last forward pass

@@ -140,7 +140,7 @@ pbs_kernel(PbsArgs a) {
         if (a.level == 1) {
 #pragma unroll
             for (int e = 0; e < 8; e++) {
-                const int jc = t + e * TPF;
+                const int jc = first_pass_index<LOGM>(t, e);
                 uint64_t d0, d1;
                 diff_pair(ar, jc, ahat, d0, d1);
                 x[e] = make_double2(digit1_as_double(d0, dc), digit1_as_double(d1, dc));
@@ -151,7 +151,7 @@ pbs_kernel(PbsArgs a) {
         level_sel(lvl, sh, lm, thr);
 #pragma unroll
         for (int e = 0; e < 8; e++) {
-            const int jc = t + e * TPF;
+            const int jc = first_pass_index<LOGM>(t, e);
             uint64_t d0, d1;
             diff_pair(ar, jc, ahat, d0, d1);
             x[e] = make_double2(digit_as_double(d0, dc, sh, lm, thr), digit_as_double(d1, dc, sh, lm, thr));
@@ -166,7 +166,7 @@ pbs_kernel(PbsArgs a) {
         level_sel(lvl + 1, shb, lmb, thrb);
 #pragma unroll
         for (int e = 0; e < 8; e++) {
-            const int jc = t + e * TPF;
+            const int jc = first_pass_index<LOGM>(t, e);
             uint64_t d0, d1;
             diff_pair(ar, jc, ahat, d0, d1);
             xa[e] = make_double2(digit_as_double(d0, dc, sha, lma, thra), digit_as_double(d1, dc, sha, lma, thra));
@@ -267,7 +267,7 @@ pbs_kernel(PbsArgs a) {
 #endif
 #pragma unroll
                 for (int e = 0; e < 8; e++) {
-                    const int jc = t + e * TPF;                          // the key carries the 1/M of the inverse transform
+                    const int jc = first_pass_index<LOGM>(t, e);                          // the key carries the 1/M of the inverse transform
                     ac[jc] += double_to_torus(x[e].x);
                     ac[jc + M] += double_to_torus(x[e].y);
                 }
@@ -339,6 +339,8 @@ pbs_kernel_v8(PbsArgs a) {
     using C = PbsCfg8<LOGN, K, LEVEL>;
     constexpr int N = C::N, M = C::M, LOGM = C::LOGM, TPF = C::TPF, G = C::G, NF = C::NF;
     constexpr int LAST = FftPlan<LOGM>::P - 1;
+    // the table-lookup shape: first two (radix-4) levels of the M = 1024 plan fused into one 16-point pass, 2 exchanges per transform
+    constexpr bool FUSED16 = (LOGM == 10 && K == 1 && LEVEL == 2);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* acc = reinterpret_cast<uint64_t*>(smem_raw);                    // [G][N]
     double2* bufs = reinterpret_cast<double2*>(acc + (size_t)G * N);          // [NF][M] swizzled, one per interleaved transform
@@ -410,6 +412,36 @@ pbs_kernel_v8(PbsArgs a) {
             const double2* key_i = a.bsk + (size_t)i * NF * G * M + t;
 
             double2 x[NF][8], w[7];
+            if constexpr (FUSED16) {
+                // M = 1024, two levels, k = 1: a 64-thread group owns one accumulator component; its threads hold 16 points of both
+                // gadget-level transforms of that component, run the plan's two radix-4 levels without an exchange, and store
+                const int grp = t >> 6, tl = t & 63;
+                const uint64_t* ar = acc + (size_t)grp * N;
+                double2 z[LEVEL][16];
+#pragma unroll
+                for (int e = 0; e < 16; e++) {
+                    const int jc = tl + e * 64;
+                    const uint32_t s0 = (uint32_t)(jc - (int)ahat) & (2 * N - 1);
+                    const uint32_t s1 = s0 + M;
+                    const uint64_t m0 = (uint64_t)0 - (uint64_t)((s0 >> LOGN) & 1u), m1 = (uint64_t)0 - (uint64_t)((s1 >> LOGN) & 1u);
+                    const uint64_t d0 = ((ar[s0 & (N - 1)] ^ m0) - m0) - ar[jc];
+                    const uint64_t d1 = ((ar[s1 & (N - 1)] ^ m1) - m1) - ar[jc + M];
+                    double g0[LEVEL], g1[LEVEL];
+                    digits_of(d0, g0);
+                    digits_of(d1, g1);
+#pragma unroll
+                    for (int lvl = 0; lvl < LEVEL; lvl++) z[lvl][e] = make_double2(g0[lvl], g1[lvl]);
+                }
+#pragma unroll
+                for (int lvl = 0; lvl < LEVEL; lvl++) {
+                    fused16_forward(z[lvl], s_tw);
+                    double2* b = bufs + (size_t)(grp * LEVEL + lvl) * M;
+#pragma unroll
+                    for (int e = 0; e < 16; e++) b[swz(tl + e * 64)] = z[lvl][e];
+                }
+                __syncthreads();
+                fft_forward_multi_from2<LOGM, NF>(x, w, t, bufs, s_tw, wsync);
+            } else {
             load_tw<LOGM, 0>(w, t, s_tw);
             // rotation + decomposition: coefficient pairs (j, j + M) of X^ahat * acc_r - acc_r, all levels at once
 #pragma unroll
@@ -417,7 +449,7 @@ pbs_kernel_v8(PbsArgs a) {
                 const uint64_t* ar = acc + (size_t)r * N;
 #pragma unroll
                 for (int e = 0; e < 8; e++) {
-                    const int jc = t + e * TPF;
+                    const int jc = first_pass_index<LOGM>(t, e);
                     const uint32_t s0 = (uint32_t)(jc - (int)ahat) & (2 * N - 1);
                     const uint32_t s1 = s0 + M;                        // bit LOGN of s0 / s1 = sign of the wrapped coefficient
                     const uint64_t m0 = (uint64_t)0 - (uint64_t)((s0 >> LOGN) & 1u), m1 = (uint64_t)0 - (uint64_t)((s1 >> LOGN) & 1u);
@@ -431,6 +463,7 @@ pbs_kernel_v8(PbsArgs a) {
                 }
             }
             fft_forward_multi<LOGM, NF>(x, w, t, bufs, s_tw, sync, wsync);   // w now holds the last pass's twiddles
+            }
 
             // Fourier MAC, one output component at a time (fma chain over f = r * l + lvl ascending), then that spectrum's
             // first inverse pass (the same node twiddles, conjugated) and its store for the interleaved remainder
@@ -454,6 +487,23 @@ pbs_kernel_v8(PbsArgs a) {
                 pass_nodes<LOGM, LAST, true>(o, w);
                 pass_store<LOGM, LAST>(o, t, bufs + (size_t)c * M);
             }
+            if constexpr (FUSED16) {
+                fft_inverse_multi_pass2<LOGM, G>(t, bufs, s_tw, wsync);
+                __syncthreads();
+                const int grp = t >> 6, tl = t & 63;                        // group c finishes output component c
+                const double2* b = bufs + (size_t)grp * M;
+                double2 z[16];
+#pragma unroll
+                for (int e = 0; e < 16; e++) z[e] = b[swz(tl + e * 64)];
+                fused16_inverse(z, s_tw);
+                uint64_t* ac = acc + (size_t)grp * N;
+#pragma unroll
+                for (int e = 0; e < 16; e++) {
+                    const int jc = tl + e * 64;
+                    ac[jc] += double_to_torus(z[e].x);
+                    ac[jc + M] += double_to_torus(z[e].y);
+                }
+            } else {
             double2 y[G][8];
             fft_inverse_multi_rest<LOGM, G>(y, t, bufs, s_tw, sync, wsync);
 #pragma unroll
@@ -461,10 +511,11 @@ pbs_kernel_v8(PbsArgs a) {
                 uint64_t* ac = acc + (size_t)c * N;
 #pragma unroll
                 for (int e = 0; e < 8; e++) {
-                    const int jc = t + e * TPF;                          // the key carries the 1/M of the inverse transform
+                    const int jc = first_pass_index<LOGM>(t, e);                          // the key carries the 1/M of the inverse transform
                     ac[jc] += double_to_torus(y[c][e].x);
                     ac[jc + M] += double_to_torus(y[c][e].y);
                 }
+            }
             }
             __syncthreads();                                           // accumulator complete, buffers free
         }
@@ -504,7 +555,7 @@ fft_forward_kernel(const void* __restrict__ in, double2* __restrict__ out, const
         load_tw<LOGM, 0>(w, t, s_tw);
 #pragma unroll
         for (int e = 0; e < 8; e++) {
-            const int jc = t + e * TPF;
+            const int jc = first_pass_index<LOGM>(t, e);
             if (MODE == 0) {
                 const uint64_t* src = reinterpret_cast<const uint64_t*>(in) + p * N;
                 x[e] = make_double2((double)(int64_t)src[jc], (double)(int64_t)src[jc + M]);
@@ -544,7 +595,7 @@ fft_inverse_kernel(const double2* __restrict__ in, uint64_t* __restrict__ out, c
         uint64_t* dst = out + p * N;
 #pragma unroll
         for (int e = 0; e < 8; e++) {
-            const int jc = t + e * TPF;
+            const int jc = first_pass_index<LOGM>(t, e);
             dst[jc] = double_to_torus(x[e].x * (1.0 / M));
             dst[jc + M] = double_to_torus(x[e].y * (1.0 / M));
         }

@@ -249,7 +249,7 @@ ORC_API void orc_keyswitch(const uint64_t* ksk, uint32_t big_dim, uint32_t n, in
  *        multiplication by i is (re,im) -> (-im,re); by (c,c): (c*(re-im), c*(re+im)); by (-c,c): (-(c*(re+im)), c*(re-im)).
  *    The inverse node is the exact mirror (DIT with conjugated constants, then x_q = y_q * conj(rho^q)) and carries no
  *    1/R: the total factor 1/M is folded into the Fourier bootstrapping key (orc_bsk_to_fourier scales by 1/M).
- *    Pass plan (bits per pass, first pass = top index bits): log2(M)=8:{3,3,2} 9:{3,3,3} 10:{3,2,3,2} 11:{3,3,3,2}
+ *    Pass plan (bits per pass, first pass = top index bits): log2(M)=8:{3,3,2} 9:{3,3,3} 10:{2,2,3,3} 11:{3,3,3,2}
  *    12:{3,3,3,3}; other sizes: 3s then the remainder.  Node (pass p, high index h with S bits already split off) uses
  *        rho = exp(i*pi*(1 + 4*bitrev_S(h)) / (R * 2^(S+1))),
  *    rho^q = exp(i*2*pi * q*(1+4*bitrev_S(h)) / (R * 2^(S+2))) taken from cosl/sinl on the first octant + exact symmetries.
@@ -302,7 +302,7 @@ typedef struct { uint32_t N, M, logM; int npass; int wd[8]; int lo[8]; uint32_t 
 static fft_plan* plan_cache[32];
 
 static void plan_passes(int logM, int* npass, int* wd) {
-    static const int P8[] = {3, 3, 2}, P9[] = {3, 3, 3}, P10[] = {3, 2, 3, 2}, P11[] = {3, 3, 3, 2}, P12[] = {3, 3, 3, 3};
+    static const int P8[] = {3, 3, 2}, P9[] = {3, 3, 3}, P10[] = {2, 2, 3, 3}, P11[] = {3, 3, 3, 2}, P12[] = {3, 3, 3, 3};
     const int* src = 0; int n = 0;
     switch (logM) { case 8: src = P8; n = 3; break; case 9: src = P9; n = 3; break; case 10: src = P10; n = 4; break;
                     case 11: src = P11; n = 4; break; case 12: src = P12; n = 4; break; default: break; }

@@ -36,11 +36,13 @@ def test_no_cpu_fallback():
 
 
 def test_fft_tables_equal_oracle(oracle):
-    for N in (512, 1024, 2048, 4096):
+    for N in (512, 1024, 2048, 4096, 8192):
         tw = binding.fft_tables(N)
         assert np.array_equal(tw, oracle.fft_tables(N))
-        # first pass: one radix-8 node with rho = exp(i*pi/16): its 4th power is exactly (1+i)/sqrt(2)
-        assert tw[3, 0] == tw[3, 1] == np.float64(0.5) ** 0.5
+        # first pass: one radix-8 node with rho = exp(i*pi/16): its 4th power is exactly (1+i)/sqrt(2);
+        # N = 2048 (M = 1024, plan {2,2,3,3}) starts with a radix-4 node, rho = exp(i*pi/8): its 2nd power
+        q = 1 if N == 2048 else 3
+        assert tw[q, 0] == tw[q, 1] == np.float64(0.5) ** 0.5
         assert np.allclose(tw[:-1, 0] ** 2 + tw[:-1, 1] ** 2, 1.0, atol=1e-15)
 
 
