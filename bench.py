@@ -327,6 +327,12 @@ def run_gpu(args):
             "clocks": clocks,
             "roofline": pbs_roofline(dom, bit if dom == "pbs_bit" else tlu),
             "roofline_other_pbs_kernel": pbs_roofline("pbs_tlu" if dom == "pbs_bit" else "pbs_bit", tlu if dom == "pbs_bit" else bit),
+            "roofline_whole_step": {"note": "all PBS flops of this rank's share of one image (SURVEY 8(d) formula) over the device time of the step; "
+                                            "at N > 1 the chains of a layer run on several streams, so the per-class times above overlap and "
+                                            "this is the per-rank figure to compare across N",
+                                    "achieved": (cnt["tlu"] * P.pbs_flops(tlu) + cnt["bit"] * P.pbs_flops(bit)) / (1 if replicas else world) / dev_s / 1e12,
+                                    "peak": dfma / 1e12, "unit": "TFLOP/s",
+                                    "frac": (cnt["tlu"] * P.pbs_flops(tlu) + cnt["bit"] * P.pbs_flops(bit)) / (1 if replicas else world) / dev_s / dfma},
             "kernel_breakdown_s_per_step": {k: v[0] / args.steps for k, v in ks.items()},
             "kernel_breakdown_note": ("CUDA-event time per kernel class on the launching stream" +
                                       ("; with N > 1 the two halves of a layer run on two streams, so class times overlap and sum to more than the step" if world > 1 else "")),
