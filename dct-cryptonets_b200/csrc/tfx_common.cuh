@@ -140,7 +140,8 @@ __device__ __forceinline__ uint32_t mod_switch(uint64_t x, int log2_2N) {
 // saturating conversion gets wrong is y == +2^63 (must wrap to -2^63): it comes back as INT64_MAX, which no in-range y
 // can produce (doubles near 2^63 are multiples of 1024), so it is patched with integer ops (off the FP64 pipe).
 __device__ __forceinline__ uint64_t double_to_torus(double v) {
-    const double r = rint(v * 0x1p-64);
+    // rint(v * 2^-64) without the conversion pipe: adding 1.5 * 2^52 rounds to nearest even at the unit place (|v| < 2^115)
+    const double r = fma(v, 0x1p-64, 6755399441055744.0) - 6755399441055744.0;
     const double y = fma(-r, 0x1p64, v);
     const long long q = __double2ll_rn(y);
     return (uint64_t)q + (q == 0x7fffffffffffffffLL ? 1ULL : 0ULL);
