@@ -124,6 +124,8 @@ class CircuitExecutor:
         self.max_chains = (4 if world_size > 1 else 1) if env is None else max(1, int(env) if env != "1" else 2)
         self.split_streams = self.max_chains > 1
         self._sides: List[Tuple[torch.cuda.Stream, Context]] = []
+        if self.ctx.device.type == "cuda":               # one wave of the bit-extraction kernel: 4 resident CTAs per SM
+            self.WAVE_ROWS = 4 * torch.cuda.get_device_properties(self.ctx.device).multi_processor_count
         self._perm: Dict[Tuple[int, int, int], Tuple[torch.Tensor, np.ndarray]] = {}
         self._prepare_constants()
 
@@ -243,7 +245,7 @@ class CircuitExecutor:
             self._perm[key] = (torch.from_numpy(perm).to(self.ctx.device), order)
         return self._perm[key]
 
-    WAVE_ROWS = 592          # 148 SMs x 4 resident CTAs of the bit-extraction PBS kernel (2 waves of the table kernel)
+    WAVE_ROWS = 592          # default: 148 SMs x 4 resident CTAs of the bit-extraction PBS kernel (= 2 waves of the table kernel)
 
     def _side(self, i: int) -> Tuple[torch.cuda.Stream, Context]:
         while len(self._sides) <= i:

@@ -174,6 +174,19 @@ def test_parameter_picker_meets_noise_constraints(tiny):
         P.pick_parameters(spec3)
 
 
+def test_seven_bit_lookups_get_the_8192_polynomial(tiny):
+    """rounding_threshold_bits=7 (the reference's ImageNet setting, run_homomorphic_eval.sh:25): the mod-switch noise at 2N = 8192
+    alone exceeds a 7-bit lookup's budget, so the picker must move the table set to (k=1, N=8192) — served by the general PBS kernel"""
+    m, calib, _ = tiny
+    circ7 = C.build_circuit(m, calib, 5, 7, 0.01)
+    assert max(op.keep_bits for op in circ7.lookups()) == 7
+    tlu, bit, info = P.pick_parameters(circ7.noise_spec())
+    assert (tlu.k, tlu.N) == (1, 8192) and info["big_dim"] == 8192 and bit.k * bit.N <= 8192
+    assert P._check(circ7.noise_spec(), tlu, bit, P.z_score(0.01))[0]
+    with pytest.raises(ValueError):
+        P.pick_parameters(circ7.noise_spec(), big_dim=4096)
+
+
 def test_work_formulas_match_survey_examples():
     p = PbsParams(860, 1, 4096, 22, 1, 3, 3, 0.0, 0.0)
     assert abs(P.pbs_flops(p) / 0.44e9 - 1) < 0.02 and abs(P.bsk_bytes(p) / 113e6 - 1) < 0.01   # SURVEY §8(d) worked example

@@ -142,3 +142,18 @@ def test_rounding_chain_and_lookup_of_a_1536_row_slice(gpu_ctx, oracle, shipped)
     rounded = ((acc_vals[:rows_tlu].astype(np.int64) + (1 << (lsbs - 1))) >> lsbs) & ((1 << keep) - 1)
     expect = tables[idx, rounded]
     assert (dec == expect).mean() > 0.97                              # p_error = 0.01 per PBS by design
+
+
+@pytest.mark.parametrize("env", ["TFX_KS_IMMA", "TFX_KS_IMAD"], ids=["mma_sync_fallback", "integer_pipe_fallback"])
+def test_keyswitch_fallback_kernels_at_the_shipped_sets(gpu_ctx, oracle, shipped, monkeypatch, env):
+    """the tcgen05 keyswitch is the default; the mma.sync kernel (TFX_KS_IMMA=1) and the integer-pipe kernel (TFX_KS_IMAD=1) stay
+    available for gadgets / devices the tensor path cannot hold and must give the same words"""
+    monkeypatch.setenv(env, "1")
+    ks = shipped
+    rng = np.random.default_rng(70)
+    big = rng.integers(0, 2**64, size=(150, ks.big_dim + 1), dtype=np.uint64)
+    for sid, p in enumerate((TLU, BIT)):
+        got = gpu_ctx.to_host_u64(ks.keyswitch(sid, gpu_ctx.to_device_u64(big), shift=5, body_offset=1 << 62))
+        ref = oracle.keyswitch(ks.get_ksk(sid), big, p.ksk_base_log, p.ksk_level, shift=5, body_offset=1 << 62)
+        assert np.array_equal(got, ref)
+
