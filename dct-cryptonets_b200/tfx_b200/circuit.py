@@ -92,6 +92,32 @@ class FusedAddOp:
 
 
 @dataclass
+class LinOp:
+    """dst = sum_i coef_i * Tap_i(src_i): a leveled linear combination of quantised tensors that share one scale.  A term with a
+    tap (ky, kx) reads element (y * stride + ky - pad, x * stride + kx - pad) of its source (zero outside the image); a term with
+    ky = -1 is already at the output resolution.  Building block of MaxPool2d, reference models/backbone.py:153-160,252-259:
+    the running maximum is m_j = m_{j-1} + relu(t_j - m_{j-1}), i.e. r_j = relu(t_j - t_0 - r_1 - ... - r_{j-1}) as one lookup on
+    a LinOp per window element and max = t_0 + r_1 + ... + r_{k*k-1} as a last LinOp (the sources are >= 0, so the zero padding of
+    a tap equals MaxPool2d's -inf padding)."""
+    name: str
+    terms: list                 # [[source value id, coefficient, ky, kx], ...]; the first term carries a tap
+    dst: int
+    in_shape: Tuple[int, int, int]
+    shape: Tuple[int, int, int]
+    kernel: int
+    stride: int
+    pad: int
+    acc_bits: int = 0
+    offset: object = 0          # int64 [C], see ConvOp.offset
+    shifts: Optional[list] = None   # per term: log2 of the encoding shift (emitted width of the source - acc_bits)
+    chan_bits: Optional[np.ndarray] = None
+    kind: str = "lin"
+
+    def eff_coefs(self) -> List[int]:
+        return [int(c) << int(sh) for (_, c, _, _), sh in zip(self.terms, self.shifts or [0] * len(self.terms))]
+
+
+@dataclass
 class TluOp:
     name: str
     src: int                    # accumulator value (output of a conv / add)
@@ -158,7 +184,7 @@ class Circuit:
         return total
 
     def maximum_integer_bit_width(self) -> int:
-        widths = [op.acc_bits for op in self.ops if op.kind in ("conv", "add", "fadd")]
+        widths = [op.acc_bits for op in self.ops if op.kind in ("conv", "add", "fadd", "lin")]
         return max(widths + [self.input_width])
 
     def noise_spec(self, input_std: float = 2.0 ** -50) -> CircuitNoiseSpec:
@@ -170,6 +196,9 @@ class Circuit:
                 w = lin.weight.astype(np.float64)
                 norm2 = float((w.reshape(w.shape[0], -1) ** 2).sum(axis=1).max())
                 fresh = lin.src == self.input_id
+            elif lin.kind == "lin":
+                norm2 = float(sum(c * c for c in lin.eff_coefs()))
+                fresh = False
             elif lin.kind == "fadd":
                 w = producers[lin.a].weight.astype(np.float64)
                 norm2 = float((w.reshape(w.shape[0], -1) ** 2).sum(axis=1).max()) + float((np.asarray(lin.sb, dtype=np.float64) ** 2).max())
@@ -198,6 +227,10 @@ class Circuit:
             elif op.kind == "fadd":
                 lines.append(f"  %{op.dst} = fused_add(%{op.a}, %{op.b} * [{int(np.min(op.sb))}..{int(np.max(op.sb))}]/channel) "
                              f"{{offset={_offset_text(op.offset)}}} : eint<{op.acc_bits}>{list(op.shape)}   // {op.name}")
+            elif op.kind == "lin":
+                tt = " + ".join(f"{c} * %{sv}" + (f"[tap {ky},{kx}]" if ky >= 0 else "") for (sv, _, ky, kx), c in zip(op.terms, op.eff_coefs()))
+                lines.append(f"  %{op.dst} = lincomb({tt}) {{window={op.kernel}, stride={op.stride}, pad={op.pad}, offset={_offset_text(op.offset)}}} "
+                             f": eint<{op.acc_bits}>{list(op.shape)}   // {op.name}")
             elif op.kind == "add":
                 lines.append(f"  %{op.dst} = add(%{op.a} * {op.sa}, %{op.b} * {op.sb}) {{offset={_offset_text(op.offset)}}} : eint<{op.acc_bits}>{list(op.shape)}   // {op.name}")
             else:
@@ -216,7 +249,7 @@ class Circuit:
 # Serialisation: JSON header + raw arrays (no pickle: a bundle comes from the model provider and is opened by the
 # process that holds the secret key).  Unknown op kinds or fields are rejected.
 # --------------------------------------------------------------------------------------------------------
-_OP_CLASSES = {"conv": ConvOp, "add": AddOp, "fadd": FusedAddOp, "tlu": TluOp}
+_OP_CLASSES = {"conv": ConvOp, "add": AddOp, "fadd": FusedAddOp, "lin": LinOp, "tlu": TluOp}
 _TUPLE_FIELDS = {"in_shape", "out_shape", "shape", "input_shape", "output_shape"}
 
 
@@ -297,6 +330,23 @@ def _int_conv(x: np.ndarray, op: ConvOp, weight: np.ndarray) -> np.ndarray:
     groups = x.shape[1] if op.depthwise else 1
     y = F.conv2d(xt, wt, stride=op.stride, padding=op.pad, groups=groups)
     return np.rint(y.numpy()).astype(np.int64)
+
+
+def window_tap(x: np.ndarray, ky: int, kx: int, kernel: int, stride: int, pad: int) -> np.ndarray:
+    """x int64 [B][C][H][W] -> [B][C][Ho][Wo]: element (y*stride + ky - pad, x*stride + kx - pad), zero outside"""
+    B, C, H, W = x.shape
+    Ho, Wo = (H + 2 * pad - kernel) // stride + 1, (W + 2 * pad - kernel) // stride + 1
+    xp = np.zeros((B, C, H + 2 * pad, W + 2 * pad), dtype=x.dtype)
+    xp[:, :, pad:pad + H, pad:pad + W] = x
+    return np.ascontiguousarray(xp[:, :, ky:ky + (Ho - 1) * stride + 1:stride, kx:kx + (Wo - 1) * stride + 1:stride])
+
+
+def lin_apply(op: "LinOp", vals: dict) -> np.ndarray:
+    out = None
+    for sv, coef, ky, kx in op.terms:
+        v = vals[sv] if ky < 0 else window_tap(vals[sv], ky, kx, op.kernel, op.stride, op.pad)
+        out = coef * v if out is None else out + coef * v
+    return out
 
 
 def channel_offsets(offset, channels: int) -> np.ndarray:
@@ -405,6 +455,9 @@ def evaluate_clear(circ: Circuit, q_in: np.ndarray, collect: Optional[dict] = No
             offs[op.dst] = op.offset
         elif op.kind == "fadd":
             vals[op.dst] = vals[op.a] + _chan_view(op.m) * vals[op.b]
+            offs[op.dst] = op.offset
+        elif op.kind == "lin":
+            vals[op.dst] = lin_apply(op, vals)
             offs[op.dst] = op.offset
         elif noise is None:
             vals[op.dst] = tlu_apply(op, offs[op.src], vals[op.src])
@@ -668,6 +721,8 @@ class CircuitBuilder:
                     env[node] = src if not src.lin_is_acc else self._chain(src, _identity, src.affine_only, keep_affine=True)
                 elif isinstance(m, nn.AvgPool2d):
                     env[node] = self._avgpool(node, m, src, node.args[0])
+                elif isinstance(m, nn.MaxPool2d):
+                    env[node] = self._maxpool(node, m, src, node.args[0])
                 elif isinstance(m, nn.Flatten):
                     env[node] = _Sym(src.lin, src.lin_is_acc, src.scale, src.chain, (int(np.prod(src.shape)),), src.affine_only, src.affine_factor,
                                      src.quant)
@@ -763,6 +818,40 @@ class CircuitBuilder:
         f = 1.0 / (k * k)
         return _Sym(vid, True, self.qinfo[q].scale, [lambda y, f=f: y * f], op.out_shape, True, f)
 
+    def _lin(self, name: str, terms: list, in_shape, out_shape, k: int, s: int, p: int) -> "LinOp":
+        vid = self._new()
+        op = LinOp(name, [list(map(int, t)) for t in terms], vid, tuple(in_shape), tuple(out_shape), k, s, p, shifts=[0] * len(terms))
+        acc = lin_apply(op, self.ints)
+        self._finish_acc(op, acc)
+        self.ops.append(op)
+        self.ints[vid] = acc
+        self.acc_of[vid] = op
+        for idx, t in enumerate(op.terms):
+            self._register(t[0], op, f"t{idx}")
+        return op
+
+    def _maxpool(self, node, m, src: _Sym, src_key) -> _Sym:
+        """MaxPool2d on a quantised, non-negative tensor (the reference puts it after the stem ReLU, backbone.py:153-160): a chain of
+        k*k - 1 lookups r_j = relu(t_j - running maximum) over the window elements t_j, all on the source's scale (see LinOp)."""
+        q = self._materialize(src_key, src)
+        scale = self.qinfo[q].scale
+        one = lambda v: v if isinstance(v, int) else v[0]
+        k, s, p = one(m.kernel_size), one(m.stride if m.stride is not None else m.kernel_size), one(m.padding)
+        if one(m.dilation) != 1 or m.ceil_mode:
+            raise NotImplementedError("MaxPool2d with dilation or ceil_mode")
+        if p > 0 and self.ints[q].min() < 0:
+            raise NotImplementedError("padded MaxPool2d on a tensor with negative values (a tap pads with zero, MaxPool2d with -inf)")
+        c, h, w_ = self.ints[q].shape[1:]
+        out_shape = (c, (h + 2 * p - k) // s + 1, (w_ + 2 * p - k) // s + 1)
+        taps = [(ky, kx) for ky in range(k) for kx in range(k)]
+        rs: List[int] = []
+        for j in range(1, len(taps)):
+            terms = [[q, 1, *taps[j]], [q, -1, *taps[0]]] + [[r, -1, -1, -1] for r in rs]
+            d = self._lin(f"maxdiff{j}_{node.target}", terms, (c, h, w_), out_shape, k, s, p)
+            rs.append(self._materialize(("maxpool", node.name, j), _Sym(d.dst, True, scale, [torch.relu], out_shape, False), forced_scale=scale))
+        top = self._lin(f"maxpool_{node.target}", [[q, 1, *taps[0]]] + [[r, 1, -1, -1] for r in rs], (c, h, w_), out_shape, k, s, p)
+        return _Sym(top.dst, True, scale, [], out_shape)
+
     def _try_fused_add(self, node, a: _Sym, b: _Sym, ka, kb) -> Optional[_Sym]:
         """a: unmaterialised conv accumulator with a per-channel affine chain (BatchNorm); b: quantised tensor.  See FusedAddOp."""
         qb = self.materialized.get(kb) if b.lin_is_acc else (b.lin if not b.chain else None)   # b must already exist as a quantised tensor
@@ -848,6 +937,8 @@ class CircuitBuilder:
                     op.weight = (op.raw_weight.astype(np.int64) << ls).astype(np.int32)
                 elif op.kind == "fadd":
                     op.sb = op.m << ls
+                elif op.kind == "lin":
+                    op.shifts[int(role[1:])] = ls
                 elif role == "a":
                     op.sa = 1 << ls
                 else:

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from .binding import Context, KeySet, PbsParams, TfxError, launch_count
-from .circuit import Circuit, ConvOp, AddOp, TluOp, channel_offsets
+from .circuit import Circuit, ConvOp, AddOp, LinOp, TluOp, channel_offsets
 
 MASK64 = (1 << 64) - 1
 TLU_SET, BIT_SET = 0, 1
@@ -137,6 +137,15 @@ class CircuitExecutor:
             if op.kind == "conv":
                 self._weights[op.dst] = torch.from_numpy(np.ascontiguousarray(op.weight)).to(dev)
                 self._bias[op.dst] = self.ctx.to_device_u64(self._body_constants(op, op.out_shape[0]))
+            elif op.kind == "lin":
+                # one depthwise one-hot kernel per window tap, carrying the term's (shifted) coefficient
+                C = op.shape[0]
+                for idx, ((sv, _, ky, kx), ce) in enumerate(zip(op.terms, op.eff_coefs())):
+                    if ky >= 0:
+                        wk = np.zeros((C, 1, op.kernel, op.kernel), dtype=np.int32)
+                        wk[:, 0, ky, kx] = ce
+                        self._weights[(op.dst, idx)] = torch.from_numpy(wk).to(dev)
+                self._bias[op.dst] = self.ctx.to_device_u64(self._body_constants(op, C))
             elif op.kind == "tlu":
                 luts = lut_polynomials(op.tables, op.keep_bits, N_tlu, op.out_width)
                 self._luts[op.dst] = self.ctx.to_device_u64(luts)
@@ -299,7 +308,7 @@ class CircuitExecutor:
         # liveness: a layer tensor (hundreds of MB to GB) is released after its last consumer
         last_use: Dict[int, int] = {}
         for i, op in enumerate(circ.ops):
-            for src in ((op.a, op.b) if op.kind in ("add", "fadd") else (op.src,)):
+            for src in ((op.a, op.b) if op.kind in ("add", "fadd") else [t_[0] for t_ in op.terms] if op.kind == "lin" else (op.src,)):
                 last_use[src] = i
         last_use[circ.output_id] = len(circ.ops)
         for i, op in enumerate(circ.ops):
@@ -331,6 +340,25 @@ class CircuitExecutor:
                         acc = torch.empty_like(a)
                         for c in range(hi - lo):
                             timed("add", H * W, lambda: ctx.axpby(a[c], op.sa, b[c], op.sb, body_const=int(consts[lo + c]), out=acc[c]))
+                else:
+                    acc = ctx.empty_u64(0, H, W, words)
+                acc_local[op.dst] = (acc.view(-1, words), lo, hi, per)
+            elif op.kind == "lin":
+                # leveled linear combination of window taps and tensors (MaxPool2d chains, circuit.LinOp): taps are depthwise one-hot
+                # convolutions carrying the coefficient (the first one also adds the per-channel body constants), the rest axpby
+                C, H, W = op.shape
+                lo, hi, per = self._channel_range(C)
+                if hi > lo:
+                    acc = None
+                    for idx, ((sv, _, ky, kx), ce) in enumerate(zip(op.terms, op.eff_coefs())):
+                        if ky >= 0:
+                            term = timed("conv", (hi - lo) * H * W,
+                                         lambda: ctx.conv2d(vals[sv], self._weights[(op.dst, idx)], op.stride, op.pad,
+                                                            self._bias[op.dst] if acc is None else None, oc_range=(lo, hi), depthwise=True))
+                            acc = term if acc is None else timed("add", (hi - lo) * H * W, lambda: ctx.axpby(acc, 1, term, 1))
+                        else:
+                            term = vals[sv][lo:hi].contiguous()
+                            acc = timed("add", (hi - lo) * H * W, lambda: ctx.axpby(acc, 1, term, ce))
                 else:
                     acc = ctx.empty_u64(0, H, W, words)
                 acc_local[op.dst] = (acc.view(-1, words), lo, hi, per)

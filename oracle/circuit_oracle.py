@@ -102,6 +102,22 @@ def run_circuit(circ, keys: OracleKeys, in_cts: np.ndarray, collect: Optional[Di
             t0 = time.time()
             vals[op.dst] = O.conv2d(vals[op.src], op.weight, op.stride, op.pad, bias, depthwise=op.depthwise)
             t_lin += time.time() - t0
+        elif op.kind == "lin":
+            # linear combination of window taps and tensors (MaxPool2d chains): tap = depthwise one-hot convolution
+            C = op.shape[0]
+            consts = _body_constants(op.offset, lsbs_after.get(op.dst), op.acc_bits, C)
+            t0 = time.time()
+            acc = None
+            for (sv, _, ky, kx), ce in zip(op.terms, op.eff_coefs()):
+                if ky >= 0:
+                    wk = np.zeros((C, 1, op.kernel, op.kernel), dtype=np.int32)
+                    wk[:, 0, ky, kx] = ce
+                    term = O.conv2d(vals[sv], wk, op.stride, op.pad, consts if acc is None else None, depthwise=True)
+                    acc = term if acc is None else O.axpby(acc, 1, term, 1)
+                else:
+                    acc = O.axpby(acc, 1, vals[sv], ce)
+            vals[op.dst] = acc
+            t_lin += time.time() - t0
         elif op.kind == "fadd":
             consts = _body_constants(op.offset, lsbs_after.get(op.dst), op.acc_bits, op.shape[0])
             t0 = time.time()

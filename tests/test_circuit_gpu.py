@@ -211,3 +211,25 @@ def test_approximate_rounding_matches_oracle_and_clear(gpu_ctx, oracle):
     # approximate rounding: the mod-switch noise blurs every rounding threshold (that is the approximation), so the
     # decrypted features track the clear evaluation without being equal to it
     assert np.abs(dec - clear).max() <= 0.35 * max(1.0, np.abs(clear).max()), (dec, clear)
+
+
+def test_maxpool_stem_matches_oracle_and_clear(gpu_ctx, oracle):
+    """MaxPool2d stem (reference models/backbone.py:153-160) as chained relu lookups over window taps (circuit.LinOp): GPU ciphertexts
+    == oracle circuit word for word, decrypted == clear evaluator == torch's max_pool2d on the quantised activations"""
+    from oracle import circuit_oracle as CO
+    torch.manual_seed(6)
+    net = nn.Sequential(nn.Conv2d(3, 4, 3, padding=1, bias=False), nn.BatchNorm2d(4), nn.ReLU(), nn.MaxPool2d(3, stride=2, padding=1),
+                        nn.Conv2d(4, 5, 1, bias=False), nn.BatchNorm2d(5), nn.ReLU(), nn.AvgPool2d(2), nn.Flatten()).eval()
+    calib = torch.randn(32, 3, 6, 6)
+    circ = C.build_circuit(net, calib, n_bits=5, rounding_threshold_bits=6, p_error=0.01)
+    assert sum(op.kind == "lin" for op in circ.ops) == 9
+    ex = CircuitExecutor(circ, (TOY_TLU, TOY_BIT), ctx=gpu_ctx, input_std=2.0**-50)
+    ex.keygen(seed=17)
+    q_in = C.quantize_input(circ, calib[:1].numpy())[0]
+    got = gpu_ctx.to_host_u64(ex.run(ex.encrypt(q_in, enc_seed=18)))
+    keys = CO.OracleKeys((TOY_TLU, TOY_BIT), 17)
+    ref = CO.run_circuit(circ, keys, CO.encrypt_input(circ, keys, q_in, 2.0**-50, 18))
+    assert np.array_equal(got, ref)
+    clear = C.evaluate_clear(circ, q_in[None])[0]
+    assert np.array_equal(ex.decrypt(ex.run(ex.encrypt(q_in, enc_seed=18))).reshape(clear.shape), clear)
+

@@ -91,15 +91,27 @@ def _net(spread: bool = True):
     return net, torch.randn(32, 3, 4, 4)
 
 
-@pytest.mark.parametrize("mode", ["tensor_wide", "per_channel_offsets", "per_channel_widths", "approximate_widths", "fused_widths"])
+def _maxpool_net():
+    """conv stem + ReLU + MaxPool2d(3, 2, 1) (the reference's RGB-224 stem shape, models/backbone.py:153-160) + 1x1 conv + pool"""
+    torch.manual_seed(6)
+    net = nn.Sequential(nn.Conv2d(3, 4, 3, padding=1, bias=False), nn.BatchNorm2d(4), nn.ReLU(), nn.MaxPool2d(3, stride=2, padding=1),
+                        nn.Conv2d(4, 5, 1, bias=False), nn.BatchNorm2d(5), nn.ReLU(), nn.AvgPool2d(2), nn.Flatten()).eval()
+    return net, torch.randn(32, 3, 6, 6)
+
+
+@pytest.mark.parametrize("mode", ["tensor_wide", "per_channel_offsets", "per_channel_widths", "approximate_widths", "fused_widths",
+                                  "maxpool_widths"])
 def test_executor_host_logic_equals_oracle_circuit(oracle, mode):
     from oracle import circuit_oracle as CO
-    net, calib = _net(spread=not mode.startswith("fused"))      # small BatchNorm gains: the shortcut's integer weight m_c is >= 8
+    net, calib = _maxpool_net() if mode.startswith("maxpool") else _net(spread=not mode.startswith("fused"))   # small BatchNorm gains: the shortcut's integer weight m_c is >= 8
     circ = C.build_circuit(net, calib, n_bits=5, rounding_threshold_bits=6, p_error=0.01,
                            per_channel_offsets=(mode != "tensor_wide"), per_channel_widths=mode.endswith("widths"),
                            rounding_method="approximate" if mode.startswith("approximate") else "exact",
                            fuse_residual=mode.startswith("fused"))
     assert any(op.kind == "fadd" for op in circ.ops) == mode.startswith("fused")
+    assert any(op.kind == "lin" for op in circ.ops) == mode.startswith("maxpool")
+    if mode.startswith("maxpool"):
+        return _check_maxpool_circuit(oracle, CO, circ, net, calib)
     if mode.endswith("widths"):
         assert any(op.chan_bits is not None and len(set(op.chan_bits.tolist())) > 1 for op in circ.lookups())
     okeys = CO.OracleKeys((TLU, BIT), 9)
@@ -127,6 +139,34 @@ def test_executor_host_logic_equals_oracle_circuit(oracle, mode):
         else:
             got = _run_two_ranks(outs, o_cts)
             assert np.array_equal(got, want)
+
+
+def _check_maxpool_circuit(oracle, CO, circ, net, calib):
+    """MaxPool2d as chained b + relu(a - b) lookups over window taps: exact in the clear, executor == oracle evaluator word for word
+    (1 and 2 ranks), decrypted == clear"""
+    q = C.quantize_input(circ, calib[:4].numpy())
+    col = {}
+    C.evaluate_clear(circ, q, collect=col)
+    src = circ.ops[1]                                          # the stem's ReLU lookup
+    top = [op for op in circ.ops if op.kind == "lin"][-1]
+    ref = torch.nn.functional.max_pool2d(torch.from_numpy(col[src.dst].astype(np.float64)), 3, 2, 1).numpy().astype(np.int64)
+    assert np.array_equal(col[top.dst], ref)
+    c2 = C.circuit_from_portable(*C.circuit_to_portable(circ))
+    assert c2.to_text() == circ.to_text()
+    okeys = CO.OracleKeys((TLU, BIT), 9)
+    o_cts = CO.encrypt_input(circ, okeys, q[0], 2.0**-50, 10)
+    want = CO.run_circuit(circ, okeys, o_cts)
+    assert np.array_equal(CO.decrypt_output(circ, okeys, want), C.evaluate_clear(circ, q[:1])[0].reshape(-1))
+    execs = []
+    for world in (1, 2):
+        outs = []
+        for rank in range(world):
+            ex = CircuitExecutor(circ, (TLU, BIT), ctx=FakeContext(oracle), rank=rank, world_size=world, input_std=2.0**-50)
+            ex.max_chains = 1
+            ex.use_keys(FakeKeys(oracle, okeys, (TLU, BIT)))
+            outs.append(ex)
+        got = _np(outs[0].run(_pt(o_cts))) if world == 1 else _run_two_ranks(outs, o_cts)
+        assert np.array_equal(got, want)
 
 
 def _run_two_ranks(execs, o_cts):
