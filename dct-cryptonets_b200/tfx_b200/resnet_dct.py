@@ -36,6 +36,10 @@ STEMS = {
     "64_48_56": (1, 1, 0, False, None, 5),
     "64_64_56": (1, 1, 0, False, None, 5),
     "64_192_56": (1, 1, 0, False, None, 5),
+    # RGB stems with a max-pool (reference models/backbone.py:447-481): 7x7 stride-2 conv, ReLU, MaxPool2d(3, 2, padding 1)
+    "64_3_128": (7, 2, 3, True, (3, 2), 3),
+    "64_3_224": (7, 2, 3, True, (3, 2), 7),
+    "64_3_448": (7, 2, 3, True, (3, 2), 14),
 }
 
 

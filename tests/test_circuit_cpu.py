@@ -280,6 +280,12 @@ def test_topology_matches_reference_modules():
         x = torch.randn(2, 24, 16, 16)
         assert torch.allclose(ours(x), ref(x), atol=1e-5)
         assert ours.final_feat_dim == ref.final_feat_dim
+        # the RGB stem with a max-pool (backbone.py:447-455: 7x7 stride-2 conv, ReLU, MaxPool2d(3, 2, 1)), ResNet-18
+        ref18 = backbone.ResNet18(in_channels=3, img_size=128).eval()
+        ours18 = resnet18_dct(3, 128).eval()
+        ours18.load_state_dict(ref18.state_dict(), strict=True)
+        x = torch.randn(1, 3, 128, 128)
+        assert torch.allclose(ours18(x), ref18(x), atol=1e-5)
     finally:
         sys.path.remove(REF)
         for k, v in saved.items():
