@@ -13,10 +13,14 @@
 
 namespace tfx {
 
-constexpr int KU_M = 128, KU_N = 256, KU_K = 128, KU_STAGES = 4, KU_UMMA_K = 32;
+constexpr int KU_M = 128, KU_N = 256, KU_K = 128, KU_UMMA_K = 32;
 constexpr int KU_THREADS = 192;                                    // 6 warps
 constexpr uint32_t KU_A_BYTES = KU_M * KU_K, KU_B_BYTES = KU_N * KU_K, KU_STAGE_BYTES = KU_A_BYTES + KU_B_BYTES;
-constexpr size_t KU_SMEM = (size_t)KU_STAGES * KU_STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+// Pipeline depth: 4 stages (193 KB, one CTA per SM) for full-size batches; 1 stage (50 KB) for the small batches of a rank's
+// wave-sized chains, which run beside PBS kernels of other streams: a 193 KB CTA only fits once ALL PBS CTAs of an SM have retired
+// (measured: the keyswitch of a 592-row chunk waited 2-8 ms for an SM, profiles/r02_experiments.md 5), a 50 KB CTA takes the
+// place of the first PBS CTA that exits.
+constexpr size_t ku_smem(int stages) { return (size_t)stages * KU_STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */; }
 
 struct KuArgs {
     const uint64_t* corr; const uint64_t* in; uint64_t* out;
@@ -39,6 +43,7 @@ __device__ __forceinline__ uint64_t ku_desc(uint32_t smem_addr) {
            ((uint64_t)2 << 61);
 }
 
+template <int KU_STAGES>
 __global__ void __launch_bounds__(KU_THREADS, 1)
 keyswitch_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, KuArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -186,13 +191,17 @@ int launch_keyswitch_umma(const KsLaunch& p, cudaStream_t stream) {
     CUtensorMap ma, mb;
     if (!make_map(&ma, p.digits, p.count, kp, KU_M) || !make_map(&mb, p.ksk_bytes, (uint64_t)npad * 8, kp, KU_N))
         return set_error(TFX_ERR_UNSUPPORTED, "keyswitch: cuTensorMapEncodeTiled failed");
-    cudaError_t e = cudaFuncSetAttribute(keyswitch_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KU_SMEM);
+    const bool small = p.count <= 2048 && !getenv("TFX_KS_DEEP");          // TFX_KS_DEEP=1: measurement knob, always 4 stages
+    const size_t smem = ku_smem(small ? 1 : 4);
+    cudaError_t e = small ? cudaFuncSetAttribute(keyswitch_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                          : cudaFuncSetAttribute(keyswitch_umma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(keyswitch_umma)");
     KuArgs a;
     a.corr = p.ksk + (size_t)p.big_dim * p.level * npad; a.in = p.in; a.out = p.out; a.big_dim = p.big_dim; a.n = p.n;
     a.k_stages = (uint32_t)(kp / KU_K); a.shift = p.shift; a.body_offset = p.body_offset; a.count = (uint32_t)p.count;
     dim3 grid(npad * 8 / KU_N, (unsigned)((p.count + KU_M - 1) / KU_M));
-    keyswitch_umma_kernel<<<grid, KU_THREADS, KU_SMEM, stream>>>(ma, mb, a);
+    if (small) keyswitch_umma_kernel<1><<<grid, KU_THREADS, smem, stream>>>(ma, mb, a);
+    else keyswitch_umma_kernel<4><<<grid, KU_THREADS, smem, stream>>>(ma, mb, a);
     count_launch();
     return check_launch("keyswitch_umma_kernel");
 }

@@ -263,20 +263,28 @@ class CircuitExecutor:
                 self._sides.append((st, Context(self.ctx.device.index)))   # binds to the side stream; own scratch + hand-out counter
         return self._sides[i]
 
-    def _chunks(self, nloc: int) -> List[Tuple[int, int]]:
-        """row ranges of the concurrent chains: whole waves per chunk, at most max_chains chunks"""
+    def _chunks(self, nloc: int) -> Tuple[List[Tuple[int, int]], Optional[Tuple[int, int]]]:
+        """(row ranges of the concurrent chains, row range of the chain that runs ahead or None).
+        The chains are whole waves of the bit-extraction kernel (WAVE_ROWS) each, at most max_chains of them.  What is left over a
+        whole number of table-kernel waves (WAVE_ROWS / 2 ciphertexts; the table lookup is the LAST launch of a layer, 7 ms per
+        ciphertext) becomes a small chain of its own that is enqueued completely before the others: its lookup runs early, beside
+        the other chains' extraction steps, and the lookups that end the layer fill the GPU exactly instead of leaving a partial
+        last wave to drain before the all-gather."""
         if self.max_chains <= 1 or nloc <= self.WAVE_ROWS:
-            return [(0, nloc)]
-        mode = os.environ.get("TFX_CHUNK_MODE", "wave")
+            return [(0, nloc)], None
+        mode = os.environ.get("TFX_CHUNK_MODE", "ahead")
         if mode == "equal":
             per = -(-nloc // self.max_chains)
-            return [(r0, min(nloc, r0 + per)) for r0 in range(0, nloc, per)]
-        waves = -(-nloc // self.WAVE_ROWS)
-        per = -(-waves // self.max_chains) * self.WAVE_ROWS
-        if mode == "small_first":                        # the partial chunk leads, whole-wave chunks finish the layer
-            first = nloc % per or per
-            return [(0, first)] + [(r0, r0 + per) for r0 in range(first, nloc, per)]
-        return [(r0, min(nloc, r0 + per)) for r0 in range(0, nloc, per)]
+            return [(r0, min(nloc, r0 + per)) for r0 in range(0, nloc, per)], None
+        ahead = None
+        body = nloc
+        if mode == "ahead":
+            rem = nloc % (self.WAVE_ROWS // 2)
+            if 0 < rem < nloc:
+                ahead, body = (nloc - rem, nloc), nloc - rem          # the narrowest channels (rows are sorted widest first)
+        waves = -(-body // self.WAVE_ROWS)
+        per = -(-waves // max(1, self.max_chains - (1 if ahead else 0))) * self.WAVE_ROWS
+        return [(r0, min(body, r0 + per)) for r0 in range(0, body, per)], ahead
 
     def _gather(self, local: torch.Tensor, C: int, per: int, hw: int) -> torch.Tensor:
         return gather_channels(local, C, per, hw, self.world, self.pg)
@@ -426,15 +434,21 @@ class CircuitExecutor:
                                 timed("ks_tlu", g1 - g0, lambda: keys.keyswitch(TLU_SET, src[g0:g1], shift=w - wv, out=small[g0 - r0: g1 - r0], ctx=c_))
                         timed("pbs_tlu", r1 - r0, lambda: keys.pbs(TLU_SET, small, self._luts[op.dst], idx_rows[r0:r1], out=out[r0:r1], ctx=c_))
 
-                    chunks = self._chunks(nloc)
-                    if len(chunks) > 1:
+                    chunks, ahead = self._chunks(nloc)
+                    if len(chunks) > 1 or ahead is not None:
                         # one stream per chunk; the steps are enqueued round-robin over the chunks so that the chains advance
                         # together (the GPU serves older grids first): a chunk's partial last wave is filled by the next chunk's
                         # CTAs of the same step, and the first chunk's next step is queued by the time the last chunk drains
                         main = torch.cuda.current_stream(ctx.device)
-                        lanes = [(main, ctx)] + [self._side(i) for i in range(len(chunks) - 1)]
+                        lanes = [(main, ctx)] + [self._side(i) for i in range(len(chunks) - 1 + (1 if ahead else 0))]
                         for st, _ in lanes[1:]:
                             st.wait_stream(main)                     # acc / out are produced / allocated on the main stream
+                        if ahead is not None:                        # the leftover chain runs ahead, complete, on the last lane
+                            st, sctx = lanes[-1]
+                            with torch.cuda.stream(st):
+                                for b in range(len(steps)):
+                                    bit_step(sctx, ahead[0], ahead[1], b)
+                                lookup_step(sctx, ahead[0], ahead[1])
                         for b in range(len(steps)):
                             for (st, sctx), (r0, r1) in zip(lanes, chunks):
                                 with torch.cuda.stream(st):

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--json", default=None)
     ap.add_argument("--breakdown", action="store_true", help="per-kernel-class CUDA-event sums of one more run")
     ap.add_argument("--layers", action="store_true", help="per-layer seconds against 1/world of the single-GPU layer time")
+    ap.add_argument("--timeline", default=None, help="write (class, units, start ms, end ms) of every launch of one more run to this JSON file")
     args = ap.parse_args()
     _, circ, params, info, image = bench.build_circuit_and_params()
     ctx = Context(0)
@@ -71,6 +72,14 @@ def main():
                 row["profiled_seconds"] = e0.elapsed_time(e1) / 1e3
                 row["classes"] = {k: [round(v[0], 4), v[1], v[2]] for k, v in ks.items()}
                 row["class_sum"] = sum(v[0] for v in ks.values())
+            if args.timeline:
+                from tfx_b200.executor import RunStats
+                st = RunStats()
+                ref = torch.cuda.Event(enable_timing=True); ref.record()
+                ex.run(cts, st, profile_kernels=True)
+                torch.cuda.synchronize()
+                tl = [(cls, int(u), ref.elapsed_time(a), ref.elapsed_time(b)) for cls, a, b, u in st.kernel_events]
+                json.dump(tl, open(f"{args.timeline}.w{world}.c{split}.json", "w"))
             if args.layers:
                 st = RunStats()
                 ex.run(cts, st, time_layers=True)
