@@ -50,3 +50,25 @@ def test_pbs_supported_matrix():
     lib = binding.load_library()
     assert lib.tfx_pbs_supported(4096, 1) == 1 and lib.tfx_pbs_supported(2048, 2) == 1
     assert lib.tfx_pbs_supported(4096, 3) == 0 and lib.tfx_pbs_supported(100, 1) == 0
+
+
+def test_reference_arm_prints_the_contract_line_with_all_host_threads(tmp_path):
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the GPU arm): one JSON line with impl / metric / value / e2e /
+    cpu_baseline, and it must use every host core even when torch.distributed.run has exported OMP_NUM_THREADS=1 (round 1 ran
+    single-threaded under torchrun and timed out)."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0",
+                        "--cpu-sample", "16"], capture_output=True, text=True, timeout=600, env=env, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "encrypted_image_latency" and line["unit"] == "s/image"
+    assert line["higher_is_better"] is False and line["value"] > 0 and line["e2e"]["value"] == line["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] == "port"
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    assert line["cpu_baseline"]["cores"] == cores
+    # the other ranks exit without work and without output
+    r1 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                        capture_output=True, text=True, timeout=120, env=dict(env, RANK="1", LOCAL_RANK="1"), cwd=str(tmp_path))
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
